@@ -1,0 +1,140 @@
+"""
+Generates tests/golden/*.npz by running the UNMODIFIED reference code that is
+runnable in the build container (see oracle/ref_loader.py).  Run from the repo
+root in a container that has /root/reference:
+
+    python -m oracle.make_golden
+
+The committed .npz files are what travels to the GPU box; this script is the
+provenance record.  Test infrastructure only.
+"""
+
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from oracle import ref_loader
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def make_apply_case(seed=1234, n=400, m=300, n_extra=5):
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(0, 10, n)
+    counts[:4] = [0, 1, 2, 9]
+    counts[-1] = 0
+    indptr = np.r_[0, np.cumsum(counts)].astype(np.int64)
+    nnz = int(indptr[-1])
+    indices = rng.integers(0, m, nnz).astype(np.int64)
+    data = rng.random(nnz)
+    # exact zero weights, an all-zero row, duplicated weights (ties in max_overlap)
+    data[rng.random(nnz) < 0.05] = 0.0
+    r = 7
+    data[indptr[r] : indptr[r + 1]] = 0.0
+    r = 9
+    data[indptr[r] : indptr[r + 1]] = 0.25
+    src = np.empty((n_extra, m))
+    src[0] = rng.random(m) + 0.1  # strictly positive
+    src[1] = rng.random(m)
+    src[1, rng.random(m) < 0.2] = np.nan  # NaNs
+    src[2] = rng.integers(0, 4, m).astype(float)  # ties -> mode, zeros
+    src[3] = rng.normal(size=m)  # negatives
+    src[3, rng.random(m) < 0.1] = 0.0
+    src[4] = np.nan  # everything missing
+    return dict(indptr=indptr, indices=indices, data=data, source=src, n=n, m=m)
+
+
+def golden_apply(ns):
+    case = make_apply_case()
+    A = ns.sparse.MatrixCSR(
+        case["data"], case["indices"], case["indptr"], case["n"], case["m"], int(case["indptr"][-1])
+    )
+    out = dict(case)
+    methods = dict(ns.reduce.ABSOLUTE_OVERLAP_METHODS)
+    methods.update(ns.reduce.RELATIVE_OVERLAP_METHODS)
+    for name, func in methods.items():
+        f = ns.make_regrid(func)
+        out["out_" + name] = f(case["source"], A, case["n"])
+        print("apply", name)
+    for p in (0.0, 33.3, 100.0):
+        f = ns.make_regrid(ns.reduce.create_percentile_method(p))
+        out[f"out_percentile_{p}"] = f(case["source"], A, case["n"])
+    # integer source (fixtures use np.arange ints: fixture_regridder.py:96)
+    isrc = np.arange(case["m"] * 2, dtype=np.int64).reshape(2, case["m"])
+    out["int_source"] = isrc
+    out["out_int_mean"] = ns.make_regrid(ns.reduce.mean)(isrc, A, case["n"])
+    np.savez_compressed(os.path.join(OUT, "apply_golden.npz"), **out)
+
+
+def golden_coo(ns):
+    rng = np.random.default_rng(77)
+    size, m = 250, 180
+    keep = rng.random(size) < 0.8
+    row = np.arange(size, dtype=np.int64)[keep]
+    col = rng.integers(0, m, row.size).astype(np.int64)
+    src = rng.random((3, m))
+    src[1, ::7] = np.nan
+    A = ns.sparse.MatrixCOO(np.ones(row.size), row, col, size, m, row.size)
+    out = ns.coo_regrid(src, A, size)
+    indptr = ns.sparse.MatrixCOO.from_triplet(row, col, np.ones(row.size), n=size, m=m).to_csr().indptr
+    np.savez_compressed(
+        os.path.join(OUT, "coo_golden.npz"), row=row, col=col, source=src, size=size, out=out, indptr=indptr
+    )
+
+
+def mixed_mesh(seed=5, nx=9, ny=7):
+    """jittered lattice, cells kept as quads or split into two triangles"""
+    rng = np.random.default_rng(seed)
+    gx, gy = np.meshgrid(np.arange(nx + 1.0), np.arange(ny + 1.0))
+    x = gx + rng.uniform(-0.2, 0.2, gx.shape)
+    y = gy + rng.uniform(-0.2, 0.2, gy.shape)
+    idx = np.arange((nx + 1) * (ny + 1)).reshape(ny + 1, nx + 1)
+    faces = []
+    for j in range(ny):
+        for i in range(nx):
+            a, b, c, d = idx[j, i], idx[j, i + 1], idx[j + 1, i + 1], idx[j + 1, i]
+            u = rng.random()
+            if u < 0.4:
+                faces.append([a, b, c, d])
+            elif u < 0.7:
+                faces.append([a, b, c, -1])
+                faces.append([a, c, d, -1])
+            else:
+                faces.append([a, b, d, -1])
+                faces.append([b, c, d, -1])
+    return np.column_stack([x.ravel(), y.ravel()]), np.array(faces, dtype=np.int64)
+
+
+def golden_connectivity(ns):
+    xy, faces = mixed_mesh()
+    area = ns.connectivity.area(faces, xy[:, 0], xy[:, 1])
+    cent = ns.connectivity.centroids(faces, xy[:, 0], xy[:, 1])
+    tri = faces[faces[:, 3] == -1][:, :3]
+    tri_area = ns.connectivity.area(tri, xy[:, 0], xy[:, 1])
+    tri_cent = ns.connectivity.centroids(tri, xy[:, 0], xy[:, 1])
+    # a clockwise copy: reference counterclockwise() (connectivity.py:396-405)
+    cw = faces.copy()
+    for r in range(0, len(cw), 3):
+        n = 4 if cw[r, 3] != -1 else 3
+        cw[r, :n] = cw[r, :n][::-1]
+    ccw = ns.connectivity.counterclockwise(cw, xy)
+    np.savez_compressed(
+        os.path.join(OUT, "connectivity_golden.npz"),
+        xy=xy, faces=faces, area=area, centroids=cent, tri=tri, tri_area=tri_area,
+        tri_centroids=tri_cent, cw=cw, ccw=ccw,
+    )
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_loader.load()
+    golden_apply(ns)
+    golden_coo(ns)
+    golden_connectivity(ns)
+    print("golden vectors written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1155 @@
+/*
+ * xg_oracle.c -- CPU ORACLE for the xugrid regridding hot path.
+ *
+ * THIS FILE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, the
+ * smoke() check in __graft_entry__.py and the cpu_baseline / --impl reference
+ * legs of bench.py may load it.  The product (xugrid_b200) never imports,
+ * links or calls anything in oracle/.
+ *
+ * What it restates
+ * ----------------
+ * Stage (2) -- weight application -- follows code that IS in /root/reference:
+ *   xugrid/regrid/regridder.py:34-69     make_regrid()._regrid  (CSR apply)
+ *   xugrid/regrid/regridder.py:400-409   CentroidLocatorRegridder._regrid
+ *   xugrid/regrid/reduce.py:16-272       the reductions
+ *   xugrid/regrid/nanpercentile.py       (selection of the k-th / k+1-th value)
+ *   xugrid/core/sparse.py:61-78          COO -> CSR (bincount + cumsum)
+ *   xugrid/ugrid/connectivity.py:372-382,615-664  close_polygons / area / centroids
+ *   xugrid/regrid/unstructured.py:17-57  replace_interpolated_weights
+ * These are pinned against the reference itself: oracle/make_golden.py runs
+ * the reference's numba code (imported from /root/reference in the build
+ * container) and commits the outputs under tests/golden/.
+ *
+ * Stage (1) -- weight construction -- lives in the THIRD-PARTY package
+ * numba_celltree (pinned >=0.4.2 by /root/reference/pyproject.toml:44,84,
+ * locked 0.4.2 in pixi.lock:13963-13976).  Its source is not under
+ * /root/reference and the package is not installable here (no network), so
+ * this file restates its PUBLISHED algorithm (Garth & Joy 2010 cell tree /
+ * bounding interval hierarchy; Sutherland-Hodgman 1974; separating axis
+ * theorem; W. R. Franklin's pnpoly; Wachspress coordinates) anchored on the
+ * reference's own call sites and mirrors:
+ *   xugrid/ugrid/ugrid2d.py:908-921      CellTree2d(vertices, faces, fill)
+ *   xugrid/regrid/unstructured.py:124-132 intersect_faces(vertices, faces, fill)
+ *   xugrid/regrid/unstructured.py:138-139 locate_points(points, tolerance)
+ *   xugrid/ugrid/ugrid2d.py:1078          compute_barycentric_weights
+ *   xugrid/ugrid/burn.py:34-56            in_bounds()  (mirror of celltree's)
+ *   xugrid/ugrid/snapping.py:223-244      to_vector / left_of (mirror)
+ *   xugrid/ugrid/ugridbase.py:1165-1170   default tolerance = 1e-12 * max bbox diagonal
+ * and pinned by the reference's known-answer tests
+ *   tests/test_ugrid2d.py:724-730,751-791,794-825
+ *   tests/test_regrid/test_unstructured.py:32-59
+ * PARITY UNPINNED for: the exact cell-tree node layout and therefore the
+ * within-row traversal order of intersect_faces, which face wins for a point
+ * exactly on a shared edge, and last-bit rounding of areas.  None of those is
+ * observable through the reference's own tests (they compare order-insensitive
+ * and with allclose).
+ *
+ * Build: see oracle/Makefile (gcc -O2 -fopenmp -ffp-contract=off).
+ * -ffp-contract=off matters: numba/LLVM does not fuse a*b+c on x86 without
+ * fastmath, and the CUDA side is compiled with -fmad=false for the same reason.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef int64_t i64;
+
+#define XO_FILL (-1)
+#define XO_MAX_N_VERTEX 32
+#define XO_STACK 256
+
+/* ------------------------------------------------------------------ */
+/* small geometry helpers (numba_celltree geometry_utils restated)     */
+/* ------------------------------------------------------------------ */
+
+typedef struct { double x, y; } pt;
+
+static inline pt to_vector(pt a, pt b) { pt v = { b.x - a.x, b.y - a.y }; return v; }
+static inline double cross2(pt u, pt v) { return u.x * v.y - u.y * v.x; }
+static inline double dot2(pt u, pt v) { return u.x * v.x + u.y * v.y; }
+
+/* a minimal polygon is a triangle; the first fill value after that ends it */
+static inline int polygon_length(const i64 *face, int k)
+{
+    for (int i = 3; i < k; ++i)
+        if (face[i] == XO_FILL) return i;
+    return k;
+}
+
+static inline int copy_vertices(const double *xy, const i64 *face, int k, pt *out)
+{
+    int n = polygon_length(face, k);
+    for (int i = 0; i < n; ++i) {
+        out[i].x = xy[2 * face[i]];
+        out[i].y = xy[2 * face[i] + 1];
+    }
+    return n;
+}
+
+int xo_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void xo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* bb = [xmin, xmax, ymin, ymax] per face (celltree bb_coords layout) */
+void xo_build_bboxes(const double *xy, const i64 *faces, i64 n_face, int k, double *bb)
+{
+#pragma omp parallel for schedule(static)
+    for (i64 f = 0; f < n_face; ++f) {
+        const i64 *face = faces + f * k;
+        double xmin, xmax, ymin, ymax;
+        xmin = xmax = xy[2 * face[0]];
+        ymin = ymax = xy[2 * face[0] + 1];
+        for (int i = 1; i < k; ++i) {
+            i64 idx = face[i];
+            if (idx == XO_FILL) break;
+            double x = xy[2 * idx], y = xy[2 * idx + 1];
+            xmin = fmin(xmin, x); xmax = fmax(xmax, x);
+            ymin = fmin(ymin, y); ymax = fmax(ymax, y);
+        }
+        bb[4 * f] = xmin; bb[4 * f + 1] = xmax; bb[4 * f + 2] = ymin; bb[4 * f + 3] = ymax;
+    }
+}
+
+/* Force counter-clockwise orientation in place: the first non-collinear
+ * consecutive vertex triple decides; a clockwise face has its first `length`
+ * entries reversed. (celltree ctor does this for tree AND query faces; the
+ * reference relies on it: tests/test_regrid/test_regridder.py:295-332.) */
+void xo_counter_clockwise(const double *xy, i64 *faces, i64 n_face, int k)
+{
+#pragma omp parallel for schedule(static)
+    for (i64 f = 0; f < n_face; ++f) {
+        i64 *face = faces + f * k;
+        int length = polygon_length(face, k);
+        pt a = { xy[2 * face[length - 2]], xy[2 * face[length - 2] + 1] };
+        pt b = { xy[2 * face[length - 1]], xy[2 * face[length - 1] + 1] };
+        for (int i = 0; i < length; ++i) {
+            pt c = { xy[2 * face[i]], xy[2 * face[i] + 1] };
+            double product = cross2(to_vector(a, b), to_vector(a, c));
+            if (product == 0.0) {
+                a = b; b = c;
+            } else {
+                if (product < 0.0) {
+                    int end = length - 1;
+                    for (int j = 0; j < length / 2; ++j) {
+                        i64 t = face[j]; face[j] = face[end - j]; face[end - j] = t;
+                    }
+                }
+                break;
+            }
+        }
+    }
+}
+
+static inline int boxes_intersect(const double *a, const double *b)
+{
+    /* strict: boxes that only touch do not intersect */
+    return a[0] < b[1] && b[0] < a[1] && a[2] < b[3] && b[2] < a[3];
+}
+
+/* ------------------------------------------------------------------ */
+/* separating axis test                                                */
+/* ------------------------------------------------------------------ */
+static inline int is_separating_axis(pt n, const pt *a, int na, const pt *b, int nb)
+{
+    double mina = INFINITY, maxa = -INFINITY, minb = INFINITY, maxb = -INFINITY;
+    for (int i = 0; i < na; ++i) {
+        double p = dot2(a[i], n);
+        mina = fmin(mina, p); maxa = fmax(maxa, p);
+    }
+    for (int i = 0; i < nb; ++i) {
+        double p = dot2(b[i], n);
+        minb = fmin(minb, p); maxb = fmax(maxb, p);
+    }
+    if (maxa > minb && maxb > mina) return 0;
+    return 1;
+}
+
+static int polygons_intersect(const pt *a, int na, const pt *b, int nb)
+{
+    pt p = a[na - 1];
+    for (int i = 0; i < na; ++i) {
+        pt q = a[i];
+        pt n = { -(q.y - p.y), q.x - p.x };
+        p = q;
+        if (n.x == 0.0 && n.y == 0.0) continue;
+        if (is_separating_axis(n, a, na, b, nb)) return 0;
+    }
+    p = b[nb - 1];
+    for (int i = 0; i < nb; ++i) {
+        pt q = b[i];
+        pt n = { -(q.y - p.y), q.x - p.x };
+        p = q;
+        if (n.x == 0.0 && n.y == 0.0) continue;
+        if (is_separating_axis(n, a, na, b, nb)) return 0;
+    }
+    return 1;
+}
+
+int xo_polygons_intersect(const double *a, int na, const double *b, int nb)
+{
+    return polygons_intersect((const pt *)a, na, (const pt *)b, nb);
+}
+
+/* ------------------------------------------------------------------ */
+/* Sutherland-Hodgman clip area                                        */
+/* subject = query (target) face, clipper = tree (source) face, CCW.    */
+/* ------------------------------------------------------------------ */
+static inline int sh_inside(pt p, pt r, pt U)
+{
+    return U.x * (p.y - r.y) > U.y * (p.x - r.x);
+}
+
+static double polygon_area(const pt *poly, int n)
+{
+    /* fan from vertex 0; each triangle contributes abs(cross) */
+    double area = 0.0;
+    pt a = poly[0];
+    pt U = to_vector(a, poly[1]);
+    for (int i = 2; i < n; ++i) {
+        pt V = to_vector(poly[i], a);
+        area += fabs(cross2(U, V));
+        U = V;
+    }
+    return 0.5 * area;
+}
+
+static double clip_area(const pt *polygon, int n_poly, const pt *clipper, int n_clip)
+{
+    pt subject[2 * XO_MAX_N_VERTEX];
+    pt output[2 * XO_MAX_N_VERTEX];
+    int n_output = n_poly;
+    for (int i = 0; i < n_poly; ++i) output[i] = polygon[i];
+
+    pt r = clipper[n_clip - 1];
+    for (int i = 0; i < n_clip; ++i) {
+        pt s = clipper[i];
+        pt U = to_vector(r, s);
+        if (U.x == 0.0 && U.y == 0.0) continue; /* note: r is NOT advanced */
+        pt N = { -U.y, U.x };
+
+        int length = n_output;
+        for (int j = 0; j < length; ++j) subject[j] = output[j];
+        n_output = 0;
+
+        pt a = subject[length - 1];
+        int a_inside = sh_inside(a, r, U);
+        for (int j = 0; j < length; ++j) {
+            pt b = subject[j];
+            pt V = to_vector(a, b);
+            if (V.x == 0.0 && V.y == 0.0) continue;
+            int b_inside = sh_inside(b, r, U);
+            if (b_inside) {
+                if (!a_inside) {
+                    pt W = to_vector(r, a);
+                    double nw = dot2(N, W), nv = dot2(N, V);
+                    if (nv != 0.0) {
+                        double t = -nw / nv;
+                        output[n_output].x = a.x + t * V.x;
+                        output[n_output].y = a.y + t * V.y;
+                        ++n_output;
+                    }
+                }
+                output[n_output++] = b;
+            } else if (a_inside) {
+                pt W = to_vector(r, a);
+                double nw = dot2(N, W), nv = dot2(N, V);
+                if (nv != 0.0) {
+                    double t = -nw / nv;
+                    output[n_output].x = a.x + t * V.x;
+                    output[n_output].y = a.y + t * V.y;
+                    ++n_output;
+                } else {
+                    b_inside = 1;
+                    output[n_output++] = b;
+                }
+            }
+            a = b;
+            a_inside = b_inside;
+        }
+        if (n_output < 3) return 0.0;
+        r = s;
+    }
+    return polygon_area(output, n_output);
+}
+
+double xo_clip_area(const double *subj, int ns, const double *clip, int nc)
+{
+    return clip_area((const pt *)subj, ns, (const pt *)clip, nc);
+}
+
+/* ------------------------------------------------------------------ */
+/* point in polygon (pnpoly) with on-edge tolerance                    */
+/* ------------------------------------------------------------------ */
+static inline int in_bounds(pt p, pt a, pt b)
+{
+    /* /root/reference/xugrid/ugrid/burn.py:34-56 */
+    double dx = b.x - a.x, dy = b.y - a.y;
+    if (fabs(dx) >= fabs(dy)) {
+        if (dx > 0) return a.x <= p.x && p.x <= b.x;
+        return b.x <= p.x && p.x <= a.x;
+    } else {
+        if (dy > 0) return a.y <= p.y && p.y <= b.y;
+        return b.y <= p.y && p.y <= a.y;
+    }
+}
+
+/* On-edge criterion: perpendicular distance |cross| / |edge| < tolerance,
+ * evaluated without the square root as cross^2 < tol^2 * |edge|^2.
+ * Why distance and not |cross| < tol: the reference's known answers in
+ * tests/test_ugrid2d.py:778-791 (tolerance=0.01, points shifted by -0.01)
+ * expect (0.49, 1.5) ON face 2's edge (1,2)-(0,1) although |cross| there is
+ * exactly 0.01000000000000000888 > 0.01, and expect (-0.01, 0.0) OUTSIDE face 0
+ * although |cross| == 0.01 on the unit-length edge (0,1)-(0,0); together with
+ * tests/test_ugrid2d.py:724-730 (tolerance 0.011) only the length-normalised
+ * form satisfies all three.  It also matches the documented default
+ * "1e-12 x the maximum bounding-box diagonal" (ugridbase.py:1165-1170), which
+ * has the unit of a length. */
+static inline int near_edge(double twice_area, pt W, double tol)
+{
+    return twice_area * twice_area < (tol * tol) * (W.x * W.x + W.y * W.y);
+}
+
+static int point_in_polygon_or_on_edge(pt p, const pt *poly, int n, double tol)
+{
+    pt v0 = poly[n - 1];
+    pt U = to_vector(p, v0);
+    int c = 0;
+    for (int i = 0; i < n; ++i) {
+        pt v1 = poly[i];
+        pt V = to_vector(p, v1);
+        double twice_area = fabs(cross2(U, V));
+        if (near_edge(twice_area, to_vector(v0, v1), tol)) {
+            if (in_bounds(p, v0, v1)) return 1;
+        }
+        if ((v0.y > p.y) != (v1.y > p.y) &&
+            p.x < ((v1.x - v0.x) * (p.y - v0.y) / (v1.y - v0.y) + v0.x))
+            c = !c;
+        v0 = v1;
+        U = V;
+    }
+    return c;
+}
+
+int xo_point_in_polygon_or_on_edge(double px, double py, const double *poly, int n, double tol)
+{
+    pt p = { px, py };
+    return point_in_polygon_or_on_edge(p, (const pt *)poly, n, tol);
+}
+
+/* ------------------------------------------------------------------ */
+/* cell tree (bounding interval hierarchy), Garth & Joy 2010           */
+/* ------------------------------------------------------------------ */
+typedef struct {
+    i64 child;      /* index of left child; right = child + 1; -1 => leaf */
+    double Lmax;    /* max of the left child's boxes along dim  */
+    double Rmin;    /* min of the right child's boxes along dim */
+    i64 ptr, size;  /* range in bb_indices */
+    int dim;
+} xo_node;
+
+typedef struct {
+    double Max, Min, Rmin, Lmax;
+    i64 index, size;
+} xo_bucket;
+
+typedef struct xo_celltree {
+    i64 n_node, n_face;
+    int k;
+    double *xy;        /* (n_node, 2) copy */
+    i64 *faces;        /* (n_face, k) copy, CCW enforced */
+    double *bb;        /* (n_face, 4) */
+    i64 *bb_indices;   /* (n_face) */
+    xo_node *nodes;
+    i64 n_nodes, cap_nodes;
+    double bbox[4];
+    int n_buckets, cells_per_leaf;
+    i64 *scratch;      /* stable_partition temp */
+    /* result holder for variable-size query results */
+    i64 res_n;
+    i64 *res_i, *res_j;
+    double *res_a;
+    /* counters of the last query (for the byte model in the bench) */
+    i64 n_candidates;
+} xo_celltree;
+
+static i64 push_node(xo_celltree *t, i64 ptr, i64 size, int dim)
+{
+    if (t->n_nodes == t->cap_nodes) {
+        t->cap_nodes = t->cap_nodes * 2 + 16;
+        t->nodes = (xo_node *)realloc(t->nodes, sizeof(xo_node) * (size_t)t->cap_nodes);
+    }
+    xo_node *n = &t->nodes[t->n_nodes];
+    n->child = -1; n->Lmax = -1.0; n->Rmin = -1.0; n->ptr = ptr; n->size = size; n->dim = dim;
+    return t->n_nodes++;
+}
+
+static inline int centroid_test(const xo_bucket *b, i64 index, const double *bb, int dim)
+{
+    double lo = bb[4 * index + 2 * dim], hi = bb[4 * index + 2 * dim + 1];
+    double centroid = lo + 0.5 * (hi - lo);
+    return centroid < b->Max;
+}
+
+static i64 stable_partition(xo_celltree *t, i64 begin, i64 end, const xo_bucket *b, int dim)
+{
+    i64 *idx = t->bb_indices, *tmp = t->scratch;
+    i64 n_true = begin, n_false = 0;
+    for (i64 i = begin; i < end; ++i) {
+        if (centroid_test(b, idx[i], t->bb, dim)) idx[n_true++] = idx[i];
+        else tmp[n_false++] = idx[i];
+    }
+    for (i64 i = 0; i < n_false; ++i) idx[n_true + i] = tmp[i];
+    return n_true;
+}
+
+static void build(xo_celltree *t, i64 root_index, int dim, int dim_flipped)
+{
+    xo_node root = t->nodes[root_index];
+    if (root.size <= t->cells_per_leaf) return;
+
+    const double *bb = t->bb;
+    i64 *idx = t->bb_indices;
+    int nb = t->n_buckets;
+
+    /* range of the node's boxes along dim */
+    double range_Lmax = -INFINITY, range_Rmin = INFINITY;
+    for (i64 i = root.ptr; i < root.ptr + root.size; ++i) {
+        double lo = bb[4 * idx[i] + 2 * dim], hi = bb[4 * idx[i] + 2 * dim + 1];
+        if (lo < range_Rmin) range_Rmin = lo;
+        if (hi > range_Lmax) range_Lmax = hi;
+    }
+    double bucket_length = (range_Lmax - range_Rmin) / nb;
+
+    xo_bucket buckets[16];
+    for (int i = 0; i < nb; ++i) {
+        buckets[i].Max = (i + 1) * bucket_length + range_Rmin;
+        buckets[i].Min = i * bucket_length + range_Rmin;
+        buckets[i].Rmin = -1.0; buckets[i].Lmax = -1.0;
+        buckets[i].index = -1; buckets[i].size = 0;
+    }
+    /* the last bucket must take everything that is left (guards rounding) */
+    buckets[nb - 1].Max = INFINITY;
+
+    /* sort the boxes into buckets by centroid, stable */
+    i64 current = root.ptr, end = root.ptr + root.size;
+    for (int i = 0; i < nb; ++i) {
+        buckets[i].index = current;
+        if (current != end) current = stable_partition(t, current, end, &buckets[i], dim);
+        buckets[i].size = current - buckets[i].index;
+    }
+
+    /* bounds per bucket */
+    for (int i = 0; i < nb; ++i) {
+        xo_bucket *b = &buckets[i];
+        if (b->size == 0) continue;
+        double rmin = INFINITY, lmax = -INFINITY;
+        for (i64 j = b->index; j < b->index + b->size; ++j) {
+            double lo = bb[4 * idx[j] + 2 * dim], hi = bb[4 * idx[j] + 2 * dim + 1];
+            if (lo < rmin) rmin = lo;
+            if (hi > lmax) lmax = hi;
+        }
+        b->Rmin = rmin; b->Lmax = lmax;
+    }
+
+    /* special case: two boxes sharing a centroid with one cell per leaf */
+    if (t->cells_per_leaf == 1 && root.size == 2) {
+        t->nodes[root_index].Lmax = range_Lmax;
+        t->nodes[root_index].Rmin = range_Rmin;
+        i64 l = push_node(t, root.ptr, 1, !dim);
+        push_node(t, root.ptr + 1, 1, !dim);
+        t->nodes[root_index].child = l;
+        return;
+    }
+
+    /* drop empty buckets by merging their range into a neighbour */
+    xo_bucket bk[16];
+    int m = 0;
+    for (int i = 0; i < nb; ++i) {
+        if (buckets[i].size == 0) {
+            if (m > 0) bk[m - 1].Max = buckets[i].Max;
+            continue;
+        }
+        bk[m] = buckets[i];
+        if (m == 0) bk[0].Min = buckets[0].Min;
+        ++m;
+    }
+
+    if (m == 1) {
+        /* everything in one bucket: retry once along the other dimension,
+         * otherwise this node stays a leaf */
+        if (!dim_flipped) {
+            t->nodes[root_index].dim = !root.dim;
+            build(t, root_index, !dim, 1);
+        } else {
+            t->nodes[root_index].Lmax = -1.0;
+            t->nodes[root_index].Rmin = -1.0;
+        }
+        return;
+    }
+
+    /* choose the split plane between buckets with the lowest cost */
+    int plane = 1;
+    double plane_min_cost = INFINITY;
+    i64 in_left = 0;
+    double run_Lmax = -INFINITY;
+    for (int i = 1; i < m; ++i) {
+        in_left += bk[i - 1].size;
+        i64 in_right = root.size - in_left;
+        if (bk[i - 1].Lmax > run_Lmax) run_Lmax = bk[i - 1].Lmax;
+        double run_Rmin = INFINITY;
+        for (int j = i; j < m; ++j) if (bk[j].Rmin < run_Rmin) run_Rmin = bk[j].Rmin;
+        double left_volume = (run_Lmax - range_Rmin) / bucket_length;
+        double right_volume = (range_Lmax - run_Rmin) / bucket_length;
+        double cost = left_volume * (double)in_left + right_volume * (double)in_right;
+        if (i == 1 || cost < plane_min_cost) { plane_min_cost = cost; plane = i; }
+    }
+    double Lmax = -INFINITY, Rmin = INFINITY;
+    for (int i = 0; i < plane; ++i) if (bk[i].Lmax > Lmax) Lmax = bk[i].Lmax;
+    for (int i = plane; i < m; ++i) if (bk[i].Rmin < Rmin) Rmin = bk[i].Rmin;
+
+    i64 right_index = bk[plane].index;
+    i64 right_size = root.ptr + root.size - right_index;
+    i64 left_size = root.size - right_size;
+    t->nodes[root_index].Lmax = Lmax;
+    t->nodes[root_index].Rmin = Rmin;
+    i64 l = push_node(t, root.ptr, left_size, !dim);
+    i64 r = push_node(t, right_index, right_size, !dim);
+    t->nodes[root_index].child = l;
+    build(t, l, !dim, 0);
+    build(t, r, !dim, 0);
+}
+
+xo_celltree *xo_celltree_create(const double *xy, i64 n_node, const i64 *faces, i64 n_face,
+                                int k, int n_buckets, int cells_per_leaf)
+{
+    xo_celltree *t = (xo_celltree *)calloc(1, sizeof(xo_celltree));
+    t->n_node = n_node; t->n_face = n_face; t->k = k;
+    t->n_buckets = n_buckets < 2 ? 2 : (n_buckets > 16 ? 16 : n_buckets);
+    t->cells_per_leaf = cells_per_leaf < 1 ? 1 : cells_per_leaf;
+    t->xy = (double *)malloc(sizeof(double) * 2 * (size_t)(n_node > 0 ? n_node : 1));
+    memcpy(t->xy, xy, sizeof(double) * 2 * (size_t)n_node);
+    t->faces = (i64 *)malloc(sizeof(i64) * (size_t)(n_face > 0 ? n_face * k : 1));
+    memcpy(t->faces, faces, sizeof(i64) * (size_t)(n_face * k));
+    xo_counter_clockwise(t->xy, t->faces, n_face, k);
+    t->bb = (double *)malloc(sizeof(double) * 4 * (size_t)(n_face > 0 ? n_face : 1));
+    xo_build_bboxes(t->xy, t->faces, n_face, k, t->bb);
+    t->bb_indices = (i64 *)malloc(sizeof(i64) * (size_t)(n_face > 0 ? n_face : 1));
+    t->scratch = (i64 *)malloc(sizeof(i64) * (size_t)(n_face > 0 ? n_face : 1));
+    for (i64 i = 0; i < n_face; ++i) t->bb_indices[i] = i;
+    t->bbox[0] = INFINITY; t->bbox[1] = -INFINITY; t->bbox[2] = INFINITY; t->bbox[3] = -INFINITY;
+    for (i64 i = 0; i < n_face; ++i) {
+        t->bbox[0] = fmin(t->bbox[0], t->bb[4 * i]);
+        t->bbox[1] = fmax(t->bbox[1], t->bb[4 * i + 1]);
+        t->bbox[2] = fmin(t->bbox[2], t->bb[4 * i + 2]);
+        t->bbox[3] = fmax(t->bbox[3], t->bb[4 * i + 3]);
+    }
+    push_node(t, 0, n_face, 0);
+    build(t, 0, 0, 0); /* the tree build is serial in the reference too */
+    free(t->scratch); t->scratch = NULL;
+    return t;
+}
+
+void xo_celltree_destroy(xo_celltree *t)
+{
+    if (!t) return;
+    free(t->xy); free(t->faces); free(t->bb); free(t->bb_indices); free(t->nodes);
+    free(t->scratch); free(t->res_i); free(t->res_j); free(t->res_a);
+    free(t);
+}
+
+i64 xo_celltree_n_nodes(const xo_celltree *t) { return t->n_nodes; }
+i64 xo_celltree_n_candidates(const xo_celltree *t) { return t->n_candidates; }
+
+double xo_default_tolerance(const xo_celltree *t)
+{
+    double dmax = 0.0;
+    for (i64 i = 0; i < t->n_face; ++i) {
+        double dx = t->bb[4 * i + 1] - t->bb[4 * i], dy = t->bb[4 * i + 3] - t->bb[4 * i + 2];
+        double d = sqrt(dx * dx + dy * dy);
+        if (d > dmax) dmax = d;
+    }
+    return 1e-12 * dmax;
+}
+
+/* one box against the tree: count, optionally store */
+static i64 locate_box(const xo_celltree *t, const double *box, i64 *out)
+{
+    if (t->n_face == 0 || !boxes_intersect(box, t->bbox)) return 0;
+    i64 stack[XO_STACK];
+    int size = 1;
+    stack[0] = 0;
+    i64 count = 0;
+    while (size > 0) {
+        const xo_node *node = &t->nodes[stack[--size]];
+        if (node->child == -1) {
+            for (i64 i = node->ptr; i < node->ptr + node->size; ++i) {
+                i64 b = t->bb_indices[i];
+                if (boxes_intersect(box, t->bb + 4 * b)) {
+                    if (out) out[count] = b;
+                    ++count;
+                }
+            }
+        } else {
+            int dim = node->dim ? 1 : 0;
+            int left = box[2 * dim] <= node->Lmax;
+            int right = box[2 * dim + 1] >= node->Rmin;
+            if (left && right) { stack[size++] = node->child; stack[size++] = node->child + 1; }
+            else if (left) stack[size++] = node->child;
+            else if (right) stack[size++] = node->child + 1;
+        }
+    }
+    return count;
+}
+
+/* locate_boxes: count pass, cumulative sum, fill pass (as the reference) */
+static i64 locate_boxes(const xo_celltree *t, const double *boxes, i64 n_box, i64 **ii_out, i64 **jj_out)
+{
+    i64 *counts = (i64 *)malloc(sizeof(i64) * (size_t)(n_box + 1));
+    counts[0] = 0;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (i64 i = 0; i < n_box; ++i) counts[i + 1] = locate_box(t, boxes + 4 * i, NULL);
+    i64 total = 0;
+    for (i64 i = 1; i <= n_box; ++i) { total += counts[i]; counts[i] = total; }
+    i64 *ii = (i64 *)malloc(sizeof(i64) * (size_t)(total > 0 ? total : 1));
+    i64 *jj = (i64 *)malloc(sizeof(i64) * (size_t)(total > 0 ? total : 1));
+#pragma omp parallel for schedule(dynamic, 256)
+    for (i64 i = 0; i < n_box; ++i) {
+        for (i64 p = counts[i]; p < counts[i + 1]; ++p) ii[p] = i;
+        locate_box(t, boxes + 4 * i, jj + counts[i]);
+    }
+    free(counts);
+    *ii_out = ii; *jj_out = jj;
+    return total;
+}
+
+/* intersect_faces: bboxes -> locate_boxes -> SAT -> S-H area -> area > 0.
+ * Returns nnz; fetch with xo_fetch_result.  Query faces are CCW-normalised
+ * on a private copy. */
+i64 xo_intersect_faces(xo_celltree *t, const double *q_xy, i64 q_n_node, const i64 *q_faces,
+                       i64 q_n_face, int q_k)
+{
+    (void)q_n_node;
+    i64 *faces = (i64 *)malloc(sizeof(i64) * (size_t)(q_n_face * q_k > 0 ? q_n_face * q_k : 1));
+    memcpy(faces, q_faces, sizeof(i64) * (size_t)(q_n_face * q_k));
+    xo_counter_clockwise(q_xy, faces, q_n_face, q_k);
+    double *qbb = (double *)malloc(sizeof(double) * 4 * (size_t)(q_n_face > 0 ? q_n_face : 1));
+    xo_build_bboxes(q_xy, faces, q_n_face, q_k, qbb);
+    i64 *ii, *jj;
+    i64 total = locate_boxes(t, qbb, q_n_face, &ii, &jj);
+    t->n_candidates = total;
+
+    char *hit = (char *)malloc((size_t)(total > 0 ? total : 1));
+#pragma omp parallel for schedule(static)
+    for (i64 p = 0; p < total; ++p) {
+        pt a[XO_MAX_N_VERTEX], b[XO_MAX_N_VERTEX];
+        int na = copy_vertices(q_xy, faces + ii[p] * q_k, q_k, a);
+        int nb = copy_vertices(t->xy, t->faces + jj[p] * t->k, t->k, b);
+        hit[p] = (char)polygons_intersect(a, na, b, nb);
+    }
+    i64 n_hit = 0;
+    for (i64 p = 0; p < total; ++p) if (hit[p]) { ii[n_hit] = ii[p]; jj[n_hit] = jj[p]; ++n_hit; }
+    free(hit);
+
+    double *area = (double *)malloc(sizeof(double) * (size_t)(n_hit > 0 ? n_hit : 1));
+#pragma omp parallel for schedule(static)
+    for (i64 p = 0; p < n_hit; ++p) {
+        pt a[XO_MAX_N_VERTEX], b[XO_MAX_N_VERTEX];
+        int na = copy_vertices(q_xy, faces + ii[p] * q_k, q_k, a);
+        int nb = copy_vertices(t->xy, t->faces + jj[p] * t->k, t->k, b);
+        area[p] = clip_area(a, na, b, nb);
+    }
+    i64 nnz = 0;
+    for (i64 p = 0; p < n_hit; ++p)
+        if (area[p] > 0.0) { ii[nnz] = ii[p]; jj[nnz] = jj[p]; area[nnz] = area[p]; ++nnz; }
+
+    free(t->res_i); free(t->res_j); free(t->res_a);
+    t->res_i = ii; t->res_j = jj; t->res_a = area; t->res_n = nnz;
+    free(faces); free(qbb);
+    return nnz;
+}
+
+void xo_fetch_result(xo_celltree *t, i64 *ii, i64 *jj, double *area)
+{
+    memcpy(ii, t->res_i, sizeof(i64) * (size_t)t->res_n);
+    memcpy(jj, t->res_j, sizeof(i64) * (size_t)t->res_n);
+    memcpy(area, t->res_a, sizeof(double) * (size_t)t->res_n);
+}
+
+/* O(Fq * Ft) brute force, no tree: validates that the tree loses nothing */
+i64 xo_intersect_faces_bruteforce(xo_celltree *t, const double *q_xy, const i64 *q_faces,
+                                  i64 q_n_face, int q_k)
+{
+    i64 *faces = (i64 *)malloc(sizeof(i64) * (size_t)(q_n_face * q_k > 0 ? q_n_face * q_k : 1));
+    memcpy(faces, q_faces, sizeof(i64) * (size_t)(q_n_face * q_k));
+    xo_counter_clockwise(q_xy, faces, q_n_face, q_k);
+    double *qbb = (double *)malloc(sizeof(double) * 4 * (size_t)(q_n_face > 0 ? q_n_face : 1));
+    xo_build_bboxes(q_xy, faces, q_n_face, q_k, qbb);
+    i64 cap = 1024, nnz = 0;
+    i64 *ii = (i64 *)malloc(sizeof(i64) * (size_t)cap), *jj = (i64 *)malloc(sizeof(i64) * (size_t)cap);
+    double *area = (double *)malloc(sizeof(double) * (size_t)cap);
+    for (i64 i = 0; i < q_n_face; ++i) {
+        pt a[XO_MAX_N_VERTEX], b[XO_MAX_N_VERTEX];
+        int na = copy_vertices(q_xy, faces + i * q_k, q_k, a);
+        for (i64 j = 0; j < t->n_face; ++j) {
+            if (!boxes_intersect(qbb + 4 * i, t->bb + 4 * j)) continue;
+            int nb = copy_vertices(t->xy, t->faces + j * t->k, t->k, b);
+            if (!polygons_intersect(a, na, b, nb)) continue;
+            double ar = clip_area(a, na, b, nb);
+            if (!(ar > 0.0)) continue;
+            if (nnz == cap) {
+                cap *= 2;
+                ii = (i64 *)realloc(ii, sizeof(i64) * (size_t)cap);
+                jj = (i64 *)realloc(jj, sizeof(i64) * (size_t)cap);
+                area = (double *)realloc(area, sizeof(double) * (size_t)cap);
+            }
+            ii[nnz] = i; jj[nnz] = j; area[nnz] = ar; ++nnz;
+        }
+    }
+    free(t->res_i); free(t->res_j); free(t->res_a);
+    t->res_i = ii; t->res_j = jj; t->res_a = area; t->res_n = nnz;
+    free(faces); free(qbb);
+    return nnz;
+}
+
+/* point location: DFS with explicit stack, nearer child first */
+static i64 locate_point(const xo_celltree *t, pt p, double tol)
+{
+    if (t->n_face == 0) return -1;
+    i64 stack[XO_STACK];
+    int size = 1;
+    stack[0] = 0;
+    pt poly[XO_MAX_N_VERTEX];
+    while (size > 0) {
+        const xo_node *node = &t->nodes[stack[--size]];
+        if (node->child == -1) {
+            for (i64 i = node->ptr; i < node->ptr + node->size; ++i) {
+                i64 b = t->bb_indices[i];
+                int n = copy_vertices(t->xy, t->faces + b * t->k, t->k, poly);
+                if (point_in_polygon_or_on_edge(p, poly, n, tol)) return b;
+            }
+            continue;
+        }
+        int dim = node->dim ? 1 : 0;
+        double c = dim ? p.y : p.x;
+        int left = c <= node->Lmax;
+        int right = c >= node->Rmin;
+        if (left && right) {
+            if ((node->Lmax - c) < (c - node->Rmin)) {
+                stack[size++] = node->child; stack[size++] = node->child + 1;
+            } else {
+                stack[size++] = node->child + 1; stack[size++] = node->child;
+            }
+        } else if (left) stack[size++] = node->child;
+        else if (right) stack[size++] = node->child + 1;
+    }
+    return -1;
+}
+
+void xo_locate_points(const xo_celltree *t, const double *pts, i64 n, double tol, i64 *out)
+{
+    if (tol < 0) tol = xo_default_tolerance(t);
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (i64 i = 0; i < n; ++i) {
+        pt p = { pts[2 * i], pts[2 * i + 1] };
+        out[i] = locate_point(t, p, tol);
+    }
+}
+
+/* all faces containing the point (for ambiguity-aware parity checks);
+ * returns the count, writes up to cap indices ascending */
+int xo_locate_point_all(const xo_celltree *t, double px, double py, double tol, i64 *out, int cap)
+{
+    if (tol < 0) tol = xo_default_tolerance(t);
+    pt p = { px, py }, poly[XO_MAX_N_VERTEX];
+    int cnt = 0;
+    for (i64 f = 0; f < t->n_face; ++f) {
+        int n = copy_vertices(t->xy, t->faces + f * t->k, t->k, poly);
+        if (point_in_polygon_or_on_edge(p, poly, n, tol)) { if (cnt < cap) out[cnt] = f; ++cnt; }
+    }
+    return cnt;
+}
+
+/* ------------------------------------------------------------------ */
+/* barycentric weights: triangle formula if k == 3 else Wachspress      */
+/* ------------------------------------------------------------------ */
+static void bary_triangle(const pt *tri, pt p, double *w)
+{
+    pt ab = to_vector(tri[0], tri[1]);
+    pt ac = to_vector(tri[0], tri[2]);
+    pt ap = to_vector(tri[0], p);
+    double Aa = fabs(cross2(ab, ac));
+    double Ac = fabs(cross2(ab, ap));
+    double Ab = fabs(cross2(ac, ap));
+    double inv = 1.0 / Aa;
+    double wb = inv * Ab;
+    double wc = inv * Ac;
+    w[0] = 1.0 - wb - wc;
+    w[1] = wb;
+    w[2] = wc;
+}
+
+static void interp_edge_case(pt a, pt U, pt p, double *w, int n, int i, int j)
+{
+    pt V = to_vector(a, p);
+    double f = sqrt(V.x * V.x + V.y * V.y) / sqrt(U.x * U.x + U.y * U.y);
+    for (int q = 0; q < n; ++q) w[q] = 0.0;
+    w[i] = 1.0 - f;
+    w[j] = f;
+}
+
+static void bary_wachspress(const pt *poly, int n, pt p, double tol, double *w)
+{
+    double w_sum = 0.0;
+    pt a = poly[n - 1], b = poly[0];
+    pt U = to_vector(a, b);
+    pt V = to_vector(a, p);
+    double Ai = fabs(cross2(U, V));
+    if (near_edge(Ai, U, tol)) { interp_edge_case(a, U, p, w, n, n - 1, 0); return; }
+    for (int i = 0; i < n; ++i) {
+        int i_next = (i + 1) % n;
+        pt c = poly[i_next];
+        pt T = to_vector(b, c);
+        pt W = to_vector(b, p);
+        double Aj = fabs(cross2(T, W));
+        if (near_edge(Aj, T, tol)) { interp_edge_case(b, T, p, w, n, i, i_next); return; }
+        double Ci = fabs(cross2(U, T));
+        double wi = 2.0 * Ci / (Ai * Aj);
+        w[i] = wi;
+        w_sum += wi;
+        b = c; U = T; Ai = Aj;
+    }
+    for (int i = 0; i < n; ++i) w[i] /= w_sum;
+}
+
+void xo_barycentric(const xo_celltree *t, const double *pts, i64 n, double tol, i64 *idx, double *weights)
+{
+    if (tol < 0) tol = xo_default_tolerance(t);
+    int k = t->k;
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (i64 i = 0; i < n; ++i) {
+        pt p = { pts[2 * i], pts[2 * i + 1] };
+        double *w = weights + i * k;
+        for (int q = 0; q < k; ++q) w[q] = 0.0;
+        i64 f = locate_point(t, p, tol);
+        idx[i] = f;
+        if (f < 0) continue;
+        pt poly[XO_MAX_N_VERTEX];
+        int np = copy_vertices(t->xy, t->faces + f * k, k, poly);
+        if (k == 3) bary_triangle(poly, p, w);
+        else bary_wachspress(poly, np, p, tol, w);
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* connectivity.py: area / centroids                                   */
+/* ------------------------------------------------------------------ */
+void xo_face_area(const double *xy, const i64 *faces, i64 n_face, int k, double *area)
+{
+    /* connectivity.py:615-633: shoelace relative to the first vertex over the
+     * closed polygon with fill replaced by the first vertex */
+#pragma omp parallel for schedule(static)
+    for (i64 f = 0; f < n_face; ++f) {
+        const i64 *face = faces + f * k;
+        double x0 = xy[2 * face[0]], y0 = xy[2 * face[0] + 1];
+        double det = 0.0;
+        for (int i = 0; i < k; ++i) {
+            i64 ia = face[i] == XO_FILL ? face[0] : face[i];
+            i64 ib = (i + 1 < k) ? (face[i + 1] == XO_FILL ? face[0] : face[i + 1]) : face[0];
+            double ax = xy[2 * ia] - x0, ay = xy[2 * ia + 1] - y0;
+            double bx = xy[2 * ib] - x0, by = xy[2 * ib + 1] - y0;
+            det += ax * by - ay * bx;
+        }
+        area[f] = 0.5 * fabs(det);
+    }
+}
+
+void xo_face_centroid(const double *xy, const i64 *faces, i64 n_face, int k, double *cxy)
+{
+    /* connectivity.py:636-664 */
+#pragma omp parallel for schedule(static)
+    for (i64 f = 0; f < n_face; ++f) {
+        const i64 *face = faces + f * k;
+        if (k == 3) {
+            double sx = 0.0, sy = 0.0;
+            for (int i = 0; i < 3; ++i) { sx += xy[2 * face[i]]; sy += xy[2 * face[i] + 1]; }
+            cxy[2 * f] = sx / 3.0; cxy[2 * f + 1] = sy / 3.0;
+            continue;
+        }
+        double x0 = xy[2 * face[0]], y0 = xy[2 * face[0] + 1];
+        double det_sum = 0.0, cx = 0.0, cy = 0.0;
+        for (int i = 0; i < k; ++i) {
+            i64 ia = face[i] == XO_FILL ? face[0] : face[i];
+            i64 ib = (i + 1 < k) ? (face[i + 1] == XO_FILL ? face[0] : face[i + 1]) : face[0];
+            double ax = xy[2 * ia] - x0, ay = xy[2 * ia + 1] - y0;
+            double bx = xy[2 * ib] - x0, by = xy[2 * ib + 1] - y0;
+            double det = ax * by - ay * bx;
+            det_sum += det;
+            cx += (ax + bx) * det;
+            cy += (ay + by) * det;
+        }
+        double aw = 1.0 / (3.0 * det_sum);
+        cxy[2 * f] = aw * cx + x0;
+        cxy[2 * f + 1] = aw * cy + y0;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* reduce.py restated                                                  */
+/* ------------------------------------------------------------------ */
+enum {
+    XO_MEAN = 0, XO_HARMONIC_MEAN = 1, XO_GEOMETRIC_MEAN = 2, XO_SUM = 3,
+    XO_MINIMUM = 4, XO_MAXIMUM = 5, XO_MODE = 6, XO_PERCENTILE = 7,
+    XO_MAX_OVERLAP = 8, XO_CONSERVATIVE = 9
+};
+
+static double r_mean(const double *v, const double *w, int n)
+{
+    double vsum = 0.0, wsum = 0.0;
+    for (int i = 0; i < n; ++i) { if (isnan(v[i])) continue; vsum += w[i] * v[i]; wsum += w[i]; }
+    return wsum == 0 ? NAN : vsum / wsum;
+}
+static double r_harmonic(const double *v, const double *w, int n)
+{
+    double v_agg = 0.0, w_sum = 0.0;
+    for (int i = 0; i < n; ++i) {
+        if (isnan(v[i]) || v[i] == 0) continue;
+        if (w[i] > 0) { w_sum += w[i]; v_agg += w[i] / v[i]; }
+    }
+    return (v_agg == 0 || w_sum == 0) ? NAN : w_sum / v_agg;
+}
+static double r_geometric(const double *v, const double *w, int n)
+{
+    double v_agg = 0.0, w_sum = 0.0, normsum = 0.0;
+    for (int i = 0; i < n; ++i) normsum += w[i];
+    if (normsum == 0) return NAN;
+    for (int i = 0; i < n; ++i) {
+        double wi = w[i] / normsum;
+        if (v[i] > 0 && wi > 0) { v_agg += wi * log(fabs(v[i])); w_sum += wi; }
+        else if (v[i] < 0) return NAN;
+    }
+    return w_sum == 0 ? NAN : exp((1.0 / w_sum) * v_agg);
+}
+static double r_sum(const double *v, const double *w, int n)
+{
+    double v_sum = 0.0, w_sum = 0.0;
+    for (int i = 0; i < n; ++i) { if (isnan(v[i])) continue; v_sum += v[i]; w_sum += w[i]; }
+    return w_sum == 0 ? NAN : v_sum;
+}
+static double r_minimum(const double *v, const double *w, int n)
+{
+    double v_min = INFINITY, w_max = 0.0;
+    for (int i = 0; i < n; ++i) {
+        if (isnan(v[i])) continue;
+        v_min = v[i] < v_min ? v[i] : v_min;
+        w_max = w[i] > w_max ? w[i] : w_max;
+    }
+    return w_max == 0.0 ? NAN : v_min;
+}
+static double r_maximum(const double *v, const double *w, int n)
+{
+    double v_max = -INFINITY, w_max = 0.0;
+    for (int i = 0; i < n; ++i) {
+        if (isnan(v[i])) continue;
+        v_max = v[i] > v_max ? v[i] : v_max;
+        w_max = w[i] > w_max ? w[i] : w_max;
+    }
+    return w_max == 0.0 ? NAN : v_max;
+}
+static double r_mode(const double *v, const double *w, int n, double *accum)
+{
+    for (int i = 0; i < n; ++i) accum[i] = w[i];
+    int w_sum = 0;
+    double w_max = 0.0;
+    for (int i = 0; i < n; ++i) {
+        if (isnan(v[i])) continue;
+        w_max = w[i] > w_max ? w[i] : w_max;
+        w_sum += 1;
+        for (int j = 0; j < i; ++j) if (v[j] == v[i]) { accum[j] += w[i]; break; }
+    }
+    if (w_sum == 0 || w_max == 0.0) return NAN;
+    w_max = 0;
+    double mode_value = v[0];
+    for (int i = 0; i < n; ++i) {
+        if (!isnan(v[i])) {
+            if (accum[i] > w_max || (accum[i] == w_max && v[i] > mode_value)) {
+                w_max = accum[i]; mode_value = v[i];
+            }
+        }
+    }
+    return mode_value;
+}
+static double r_percentile(const double *v, const double *w, int n, double *work, double p)
+{
+    double w_max = 0.0;
+    for (int i = 0; i < n; ++i) w_max = w[i] > w_max ? w[i] : w_max;
+    if (w_max == 0.0) return NAN;
+    if (p == 0) return r_minimum(v, w, n);
+    if (p == 100) return r_maximum(v, w, n);
+    int m = 0;
+    for (int i = 0; i < n; ++i) if (!isnan(v[i])) work[m++] = v[i];
+    if (m == 0) return NAN;
+    if (m == 1) return work[0];
+    double rank = 1 + (m - 1) * p / 100.0;
+    double f = floor(rank);
+    double frac = rank - f;
+    /* nanpercentile._select_two returns the k-th and k+1-th smallest: any
+     * selection gives the same two values, so an insertion sort is used */
+    for (int i = 1; i < m; ++i) {
+        double x = work[i]; int j = i - 1;
+        while (j >= 0 && work[j] > x) { work[j + 1] = work[j]; --j; }
+        work[j + 1] = x;
+    }
+    int kk = (int)(f - 1);
+    double lower = work[kk], upper = work[kk + 1 < m ? kk + 1 : kk];
+    return lower * (1 - frac) + upper * frac;
+}
+static double r_conservative(const double *v, const double *w, int n)
+{
+    double v_agg = 0.0, w_sum = 0.0;
+    for (int i = 0; i < n; ++i) { if (isnan(v[i])) continue; v_agg += v[i] * w[i]; w_sum += w[i]; }
+    return w_sum == 0 ? NAN : v_agg;
+}
+static double r_max_overlap(const double *v, const double *w, int n)
+{
+    double w_max = 0.0, v_max = -INFINITY;
+    for (int i = 0; i < n; ++i) {
+        if (!isnan(v[i])) {
+            if (w[i] > w_max || (w[i] == w_max && v[i] > v_max)) { w_max = w[i]; v_max = v[i]; }
+        }
+    }
+    return w_max == 0.0 ? NAN : v_max;
+}
+
+static double reduce_row(int method, double p, const double *v, const double *w, int n, double *work)
+{
+    switch (method) {
+    case XO_MEAN: return r_mean(v, w, n);
+    case XO_HARMONIC_MEAN: return r_harmonic(v, w, n);
+    case XO_GEOMETRIC_MEAN: return r_geometric(v, w, n);
+    case XO_SUM: return r_sum(v, w, n);
+    case XO_MINIMUM: return r_minimum(v, w, n);
+    case XO_MAXIMUM: return r_maximum(v, w, n);
+    case XO_MODE: return r_mode(v, w, n, work);
+    case XO_PERCENTILE: return r_percentile(v, w, n, work, p);
+    case XO_MAX_OVERLAP: return r_max_overlap(v, w, n);
+    case XO_CONSERVATIVE: return r_conservative(v, w, n);
+    default: return NAN;
+    }
+}
+
+/* regridder.py:41-67.  parallel_rows == 0 keeps the reference's schedule
+ * (prange over n_extra only: one time-step runs on one core);
+ * parallel_rows == 1 also spreads rows over threads. */
+int xo_csr_apply(int method, double p, const i64 *indptr, const i64 *indices, const double *data,
+                 const double *src, i64 n_extra, i64 m, i64 n, double *out, int parallel_rows)
+{
+    i64 n_work = 0;
+    for (i64 r = 0; r < n; ++r) { i64 l = indptr[r + 1] - indptr[r]; if (l > n_work) n_work = l; }
+    if (n_work < 1) n_work = 1;
+    int ok = 1;
+    if (!parallel_rows) {
+#pragma omp parallel for schedule(static)
+        for (i64 e = 0; e < n_extra; ++e) {
+            double *ws = (double *)malloc(sizeof(double) * 2 * (size_t)n_work);
+            const double *s = src + e * m;
+            for (i64 r = 0; r < n; ++r) {
+                i64 a = indptr[r], b = indptr[r + 1];
+                int len = (int)(b - a);
+                out[e * n + r] = NAN;
+                if (len <= 0) continue;
+                for (int i = 0; i < len; ++i) ws[i] = s[indices[a + i]];
+                out[e * n + r] = reduce_row(method, p, ws, data + a, len, ws + n_work);
+            }
+            free(ws);
+        }
+    } else {
+#pragma omp parallel
+        {
+            double *ws = (double *)malloc(sizeof(double) * 2 * (size_t)n_work);
+            for (i64 e = 0; e < n_extra; ++e) {
+                const double *s = src + e * m;
+#pragma omp for schedule(static)
+                for (i64 r = 0; r < n; ++r) {
+                    i64 a = indptr[r], b = indptr[r + 1];
+                    int len = (int)(b - a);
+                    out[e * n + r] = NAN;
+                    if (len <= 0) continue;
+                    for (int i = 0; i < len; ++i) ws[i] = s[indices[a + i]];
+                    out[e * n + r] = reduce_row(method, p, ws, data + a, len, ws + n_work);
+                }
+            }
+            free(ws);
+        }
+    }
+    return ok ? 0 : -1;
+}
+
+/* regridder.py:400-409 */
+void xo_coo_gather(const i64 *row, const i64 *col, i64 nnz, const double *src, i64 n_extra, i64 m,
+                   i64 size, double *out)
+{
+#pragma omp parallel for schedule(static)
+    for (i64 e = 0; e < n_extra; ++e) {
+        for (i64 i = 0; i < size; ++i) out[e * size + i] = NAN;
+        for (i64 q = 0; q < nnz; ++q) out[e * size + row[q]] = src[e * m + col[q]];
+    }
+}
+
+/* sparse.py:61-78: rows must already be sorted */
+void xo_coo_to_csr(const i64 *row, i64 nnz, i64 n, i64 *indptr)
+{
+    for (i64 i = 0; i <= n; ++i) indptr[i] = 0;
+    for (i64 q = 0; q < nnz; ++q) indptr[row[q] + 1] += 1;
+    for (i64 i = 0; i < n; ++i) indptr[i + 1] += indptr[i];
+}
+
+/* unstructured.py:17-57 */
+void xo_replace_interpolated_weights(const double *vertices, const i64 *faces, int k,
+                                     const i64 *face_index, double *weights, i64 n,
+                                     const i64 *node_to_node_map, i64 node_index_threshold)
+{
+    for (i64 i = 0; i < n; ++i) {
+        if (face_index[i] < 0) continue; /* python would index faces[-1]; weights there are 0 */
+        const i64 *face = faces + face_index[i] * k;
+        double *wr = weights + i * k;
+        for (int j = 0; j < k; ++j) {
+            i64 p = face[j];
+            double w = wr[j];
+            if (p < node_index_threshold || w <= 0) continue;
+            i64 index = p - node_index_threshold;
+            i64 q = node_to_node_map[2 * index], r = node_to_node_map[2 * index + 1];
+            double px = vertices[2 * p], py = vertices[2 * p + 1];
+            double qx = vertices[2 * q], qy = vertices[2 * q + 1];
+            double rx = vertices[2 * r], ry = vertices[2 * r + 1];
+            double p_q = sqrt((qx - px) * (qx - px) + (qy - py) * (qy - py));
+            double p_r = sqrt((rx - px) * (rx - px) + (ry - py) * (ry - py));
+            double total = p_q + p_r;
+            double weight_q = (p_r / total) * w;
+            double weight_r = (p_q / total) * w;
+            wr[j] = 0.0;
+            for (int jj = 0; jj < k; ++jj) {
+                if (face[jj] == q) wr[jj] += weight_q;
+                if (face[jj] == r) wr[jj] += weight_r;
+            }
+        }
+    }
+}
