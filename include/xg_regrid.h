@@ -1,0 +1,158 @@
+/*
+ * xg_regrid.h -- C ABI of libxgregrid.so: the sm_100a implementation of the
+ * xugrid regridding hot path (weight construction + weight application).
+ *
+ * Conventions
+ *  - every pointer named d_* is a DEVICE pointer owned by the caller (e.g. a
+ *    torch tensor's data_ptr()); h_* is a host pointer.  The library never
+ *    keeps a caller pointer after the call returns, except xg_index, which
+ *    owns a private packed copy of the mesh.
+ *  - every function returns 0 on success or a negative xg_status; the message
+ *    of the last failure on the calling thread is xg_last_error_string().
+ *    Nothing throws, nothing falls back to the CPU.
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it.
+ *    Functions that must return a size to the host (xg_overlap_begin,
+ *    xg_index_create) synchronise that stream before returning; all others
+ *    are asynchronous.
+ *  - connectivity is (n_face, k) row-major with -1 as fill value and 0-based
+ *    node indices (what xugrid's Ugrid2d normalises to:
+ *    /root/reference/xugrid/ugrid/ugrid2d.py:103-109), as int32 or int64
+ *    (idx_bytes = 4 or 8; the reference's IntDType is intp, constants.py:10).
+ *  - coordinates are (n_node, 2) float64 row-major, i.e. Ugrid2d.node_coordinates
+ *    (/root/reference/xugrid/ugrid/ugridbase.py:576-579).
+ *  - thread safety: distinct handles / streams may be used concurrently; an
+ *    xg_index is read-only after creation and may be shared (the reference
+ *    caches its celltree the same way, ugrid2d.py:908-921).
+ *
+ * Reference interface each entry point replaces (file:line under
+ * /root/reference) is given above the declaration.
+ */
+#ifndef XG_REGRID_H
+#define XG_REGRID_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XG_ABI_VERSION 1
+
+typedef enum xg_status {
+    XG_OK = 0,
+    XG_ERR_INVALID = -1,   /* bad argument */
+    XG_ERR_CUDA = -2,      /* CUDA runtime error, see xg_last_error_string() */
+    XG_ERR_NOMEM = -3,
+    XG_ERR_UNSUPPORTED = -4 /* e.g. more than XG_MAX_N_VERTEX vertices per face */
+} xg_status;
+
+/* faces with more vertices than this are rejected (numba_celltree: MAX_N_VERTEX = 32) */
+#define XG_MAX_N_VERTEX 32
+
+/* reduction codes of xg_csr_apply: xugrid/regrid/reduce.py:254-272 */
+typedef enum xg_method {
+    XG_MEAN = 0,             /* reduce.py:16-27  */
+    XG_HARMONIC_MEAN = 1,    /* reduce.py:30-42  */
+    XG_GEOMETRIC_MEAN = 2,   /* reduce.py:45-72  */
+    XG_SUM = 3,              /* reduce.py:75-87  (unweighted!) */
+    XG_MINIMUM = 4,          /* reduce.py:90-104 */
+    XG_MAXIMUM = 5,          /* reduce.py:107-123 */
+    XG_MODE = 6,             /* reduce.py:126-158 */
+    XG_PERCENTILE = 7,       /* reduce.py:161-203, 241-251; `percentile` argument */
+    XG_MAX_OVERLAP = 8,      /* reduce.py:225-238 */
+    XG_CONSERVATIVE = 9      /* reduce.py:206-222 first_order_conservative / conductance */
+} xg_method;
+
+typedef struct xg_index xg_index;       /* spatial index over one mesh (device resident) */
+typedef struct xg_overlap xg_overlap;   /* one in-flight overlap job */
+
+int xg_abi_version(void);
+const char *xg_last_error_string(void);
+
+/* ---- spatial index -------------------------------------------------------
+ * Replaces numba_celltree.CellTree2d(vertices, faces, fill_value) as built by
+ * Ugrid2d.celltree, xugrid/ugrid/ugrid2d.py:908-921.  Faces are forced
+ * counter-clockwise internally (as CellTree2d does), the caller's arrays are
+ * not modified. */
+int xg_index_create(const double *d_xy, int64_t n_node, const void *d_faces, int idx_bytes,
+                    int64_t n_face, int k, void *stream, xg_index **out);
+int xg_index_destroy(xg_index *index);
+/* info[0]=n_face info[1]=k info[2]=levels info[3]=device bytes owned
+ * info[4]=n_node; tol = default tolerance = 1e-12 * max bbox diagonal
+ * (xugrid/ugrid/ugridbase.py:1165-1170) */
+int xg_index_info(const xg_index *index, int64_t info[8], double *default_tolerance);
+
+/* ---- overlap weights -----------------------------------------------------
+ * Replaces UnstructuredGrid2d.overlap -> CellTree2d.intersect_faces
+ * (xugrid/regrid/unstructured.py:109-135) followed by MatrixCSR.from_triplet
+ * (xugrid/core/sparse.py:61-78,119-127): all (target, source) face pairs whose
+ * Sutherland-Hodgman intersection area is > 0, as CSR over the target rows
+ * [t_begin, t_end).  The source mesh is the index; the target faces are the
+ * queries.
+ *
+ * xg_overlap_begin does the traversal and the clipping, writes
+ *   d_indptr[0 .. t_end - t_begin]  (int64, local to the range, d_indptr[0]=0)
+ * and returns nnz in *h_nnz (the stream is synchronised).  The caller then
+ * allocates indices/area of that size and calls xg_overlap_finish, which
+ * writes them with every row sorted by ascending source index (a canonical
+ * order: the reference's within-row order is its tree traversal order) and
+ * releases the job.  `relative` != 0 divides each area by the area of its
+ * source face (unstructured.py:133-134, connectivity.py:615-633). */
+int xg_overlap_begin(const xg_index *source, const double *d_t_xy, int64_t n_t_node,
+                     const void *d_t_faces, int idx_bytes, int64_t n_t_face, int k_t,
+                     int64_t t_begin, int64_t t_end, int64_t *d_indptr, int64_t *h_nnz,
+                     void *stream, xg_overlap **job);
+int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32_t *d_indices,
+                      double *d_area, int relative, void *stream);
+/* counters of the job for the byte model:
+ * stats[0]=targets stats[1]=tree-node visits (V) stats[2]=leaf bbox tests (C)
+ * stats[3]=pairs that reached the clipper (C_clip) stats[4]=nnz
+ * stats[5]=bbox candidates.  Valid after xg_overlap_begin. */
+int xg_overlap_stats(const xg_overlap *job, int64_t stats[8]);
+int xg_overlap_abort(xg_overlap *job);
+
+/* ---- point queries -------------------------------------------------------
+ * Replaces CellTree2d.locate_points(points, tolerance)
+ * (xugrid/regrid/unstructured.py:138-139, xugrid/ugrid/ugridbase.py:1305-1323,
+ * xugrid/ugrid/ugrid2d.py:1099): index of a face containing each point (ray
+ * casting, or within `tolerance` of an edge), -1 outside.  tolerance < 0
+ * selects the default.  When several faces qualify (a point on a shared
+ * edge) the smallest face index is returned. */
+int xg_locate_points(const xg_index *index, const double *d_points, int64_t n_point,
+                     double tolerance, int32_t *d_face_index, void *stream);
+/* Replaces CellTree2d.compute_barycentric_weights(points, tolerance)
+ * (xugrid/ugrid/ugrid2d.py:1054-1078): triangle formula when k == 3,
+ * Wachspress coordinates otherwise; d_weights is (n_point, k), zero for
+ * points outside and for fill slots. */
+int xg_barycentric(const xg_index *index, const double *d_points, int64_t n_point,
+                   double tolerance, int32_t *d_face_index, double *d_weights, void *stream);
+
+/* ---- per-face geometry ----------------------------------------------------
+ * connectivity.area (xugrid/ugrid/connectivity.py:615-633) and
+ * connectivity.centroids (connectivity.py:636-664). */
+int xg_face_area(const double *d_xy, const void *d_faces, int idx_bytes, int64_t n_face, int k,
+                 double *d_area, void *stream);
+int xg_face_centroid(const double *d_xy, const void *d_faces, int idx_bytes, int64_t n_face,
+                     int k, double *d_centroid_xy, void *stream);
+
+/* ---- weight application ---------------------------------------------------
+ * Replaces make_regrid(func)._regrid(source, A, size)
+ * (xugrid/regrid/regridder.py:34-69):
+ *   out[e, r] = f(src[e, indices[row r]], weights[row r])   for r in [row_begin,row_end)
+ * rows with no entries give NaN (regridder.py:63).  d_src is (n_extra, m)
+ * row-major float64; d_out is written at d_out[e * out_ld + (r - row_begin)].
+ * d_indptr is the int64 row pointer of the rows [row_begin,row_end] of ONE CSR
+ * matrix, i.e. d_indptr[r - row_begin] .. d_indptr[r - row_begin + 1] index
+ * d_indices/d_weights directly. */
+int xg_csr_apply(int method, double percentile, const int64_t *d_indptr, const int32_t *d_indices,
+                 const double *d_weights, const double *d_src, int64_t n_extra, int64_t m,
+                 int64_t n_rows, double *d_out, int64_t out_ld, void *stream);
+/* Replaces CentroidLocatorRegridder._regrid (xugrid/regrid/regridder.py:400-409):
+ *   out[e, row[q]] = src[e, col[q]], NaN elsewhere.  d_out is (n_extra, size). */
+int xg_coo_gather(const int32_t *d_row, const int32_t *d_col, int64_t nnz, const double *d_src,
+                  int64_t n_extra, int64_t m, double *d_out, int64_t size, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XG_REGRID_H */

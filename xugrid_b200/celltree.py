@@ -1,0 +1,236 @@
+"""
+GPU spatial index with the interface xugrid expects from
+``numba_celltree.CellTree2d`` (the object returned by ``Ugrid2d.celltree``,
+/root/reference/xugrid/ugrid/ugrid2d.py:908-921):
+
+* ``intersect_faces(vertices, faces, fill_value)`` -- used by
+  ``UnstructuredGrid2d.overlap`` (xugrid/regrid/unstructured.py:124-132)
+* ``locate_points(points, tolerance)`` -- unstructured.py:138-139,
+  xugrid/ugrid/ugridbase.py:1305-1323, xugrid/ugrid/ugrid2d.py:1099
+* ``compute_barycentric_weights(points, tolerance)`` -- ugrid2d.py:1054-1078
+
+All work happens in libxgregrid.so (hand-written sm_100a CUDA); torch holds
+the device memory.  numpy in -> numpy out (int64 / float64, like the
+reference); the ``*_device`` variants keep everything in HBM.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import NamedTuple, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+
+def _device(device=None) -> torch.device:
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def to_device(a: ArrayLike, dtype: Optional[torch.dtype], device: torch.device) -> torch.Tensor:
+    """numpy / torch (host or device) -> contiguous device tensor; pinned host
+    tensors are copied asynchronously."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        if t.is_cuda:
+            t = t.to(dtype)
+        else:
+            t = t.to(device, non_blocking=True).to(dtype)
+    if not t.is_cuda:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+def faces_to_device(faces: ArrayLike, fill_value: int, device: torch.device) -> torch.Tensor:
+    """(n_face, k) connectivity as int32 or int64 on the device, fill -> -1."""
+    if isinstance(faces, torch.Tensor):
+        t = faces
+    else:
+        a = np.asarray(faces)
+        if a.dtype not in (np.int32, np.int64):
+            a = a.astype(np.int64)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.dtype not in (torch.int32, torch.int64):
+        t = t.to(torch.int64)
+    if t.dim() != 2:
+        raise ValueError("faces must have shape (n_face, n_max_vertex)")
+    t = to_device(t, None, device)
+    if fill_value != -1:
+        t = torch.where(t == fill_value, torch.full_like(t, -1), t)
+    return t
+
+
+class OverlapStats(NamedTuple):
+    targets: int
+    node_visits: int
+    leaf_tests: int
+    clip_pairs: int
+    nnz: int
+    candidates: int
+
+
+class CellTree2d:
+    def __init__(self, vertices: ArrayLike, faces: ArrayLike, fill_value: int = -1, device=None):
+        L = _native.lib()
+        self.device = _device(device)
+        with torch.cuda.device(self.device):
+            self.vertices = to_device(vertices, torch.float64, self.device)
+            if self.vertices.dim() != 2 or self.vertices.shape[1] != 2:
+                raise ValueError("vertices must have shape (n_vertex, 2)")
+            self.faces = faces_to_device(faces, fill_value, self.device)
+            self.n_face, self.k = int(self.faces.shape[0]), int(self.faces.shape[1])
+            self.n_node = int(self.vertices.shape[0])
+            h = ctypes.c_void_p()
+            _native.check(
+                L.xg_index_create(
+                    _native.ptr(self.vertices), self.n_node, _native.ptr(self.faces),
+                    self.faces.element_size(), self.n_face, self.k, _native.stream_ptr(),
+                    ctypes.byref(h),
+                )
+            )
+        self._h = h
+        info = (ctypes.c_int64 * 8)()
+        tol = ctypes.c_double()
+        _native.check(L.xg_index_info(self._h, info, ctypes.byref(tol)))
+        self.n_levels = int(info[2])
+        self.device_bytes = int(info[3])
+        self.default_tolerance = float(tol.value)
+        self.last_stats: Optional[OverlapStats] = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _native.load_library().xg_index_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------ overlap
+    def intersect_faces_csr(
+        self,
+        vertices: ArrayLike,
+        faces: ArrayLike,
+        fill_value: int = -1,
+        t_begin: int = 0,
+        t_end: Optional[int] = None,
+        relative: bool = False,
+    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """
+        CSR over the target rows [t_begin, t_end): (indptr int64, indices int32,
+        area float64) device tensors, rows in ascending source index.
+        """
+        L = _native.lib()
+        with torch.cuda.device(self.device):
+            xy = to_device(vertices, torch.float64, self.device)
+            fc = faces_to_device(faces, fill_value, self.device)
+            n_t, k_t = int(fc.shape[0]), int(fc.shape[1])
+            if t_end is None:
+                t_end = n_t
+            rows = t_end - t_begin
+            indptr = torch.empty(rows + 1, dtype=torch.int64, device=self.device)
+            nnz = ctypes.c_int64()
+            job = ctypes.c_void_p()
+            s = _native.stream_ptr()
+            _native.check(
+                L.xg_overlap_begin(
+                    self._h, _native.ptr(xy), int(xy.shape[0]), _native.ptr(fc), fc.element_size(),
+                    n_t, k_t, t_begin, t_end, _native.ptr(indptr), ctypes.byref(nnz), s,
+                    ctypes.byref(job),
+                )
+            )
+            st = (ctypes.c_int64 * 8)()
+            _native.check(L.xg_overlap_stats(job, st))
+            self.last_stats = OverlapStats(*[int(st[i]) for i in range(6)])
+            indices = torch.empty(nnz.value, dtype=torch.int32, device=self.device)
+            area = torch.empty(nnz.value, dtype=torch.float64, device=self.device)
+            _native.check(
+                L.xg_overlap_finish(
+                    job, _native.ptr(indptr), _native.ptr(indices), _native.ptr(area),
+                    1 if relative else 0, s,
+                )
+            )
+        return indptr, indices, area
+
+    def intersect_faces(self, vertices: ArrayLike, faces: ArrayLike, fill_value: int = -1):
+        """numba_celltree-compatible triplets: (face index of the query mesh
+        ascending, face index of this tree, area) as numpy int64/int64/float64."""
+        indptr, indices, area = self.intersect_faces_csr(vertices, faces, fill_value)
+        counts = indptr[1:] - indptr[:-1]
+        rows = torch.repeat_interleave(
+            torch.arange(counts.numel(), device=self.device, dtype=torch.int64), counts
+        )
+        return rows.cpu().numpy(), indices.to(torch.int64).cpu().numpy(), area.cpu().numpy()
+
+    # ------------------------------------------------------------------ points
+    def locate_points_device(self, points: ArrayLike, tolerance: Optional[float] = None) -> torch.Tensor:
+        L = _native.lib()
+        with torch.cuda.device(self.device):
+            p = to_device(points, torch.float64, self.device)
+            if p.dim() != 2 or p.shape[1] != 2:
+                raise ValueError("points must have shape (n_point, 2)")
+            out = torch.empty(p.shape[0], dtype=torch.int32, device=self.device)
+            tol = -1.0 if tolerance is None else float(tolerance)
+            _native.check(
+                L.xg_locate_points(self._h, _native.ptr(p), int(p.shape[0]), tol, _native.ptr(out),
+                                   _native.stream_ptr())
+            )
+        return out
+
+    def locate_points(self, points: ArrayLike, tolerance: Optional[float] = None) -> np.ndarray:
+        return self.locate_points_device(points, tolerance).to(torch.int64).cpu().numpy()
+
+    def compute_barycentric_weights_device(self, points: ArrayLike, tolerance: Optional[float] = None):
+        L = _native.lib()
+        with torch.cuda.device(self.device):
+            p = to_device(points, torch.float64, self.device)
+            if p.dim() != 2 or p.shape[1] != 2:
+                raise ValueError("points must have shape (n_point, 2)")
+            n = int(p.shape[0])
+            idx = torch.empty(n, dtype=torch.int32, device=self.device)
+            w = torch.empty((n, self.k), dtype=torch.float64, device=self.device)
+            tol = -1.0 if tolerance is None else float(tolerance)
+            _native.check(
+                L.xg_barycentric(self._h, _native.ptr(p), n, tol, _native.ptr(idx), _native.ptr(w),
+                                 _native.stream_ptr())
+            )
+        return idx, w
+
+    def compute_barycentric_weights(self, points: ArrayLike, tolerance: Optional[float] = None):
+        idx, w = self.compute_barycentric_weights_device(points, tolerance)
+        return idx.to(torch.int64).cpu().numpy(), w.cpu().numpy()
+
+
+def face_area_device(vertices: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:
+    """connectivity.area (xugrid/ugrid/connectivity.py:615-633) on the device."""
+    L = _native.lib()
+    out = torch.empty(faces.shape[0], dtype=torch.float64, device=faces.device)
+    with torch.cuda.device(faces.device):
+        _native.check(
+            L.xg_face_area(_native.ptr(vertices), _native.ptr(faces), faces.element_size(),
+                           int(faces.shape[0]), int(faces.shape[1]), _native.ptr(out),
+                           _native.stream_ptr())
+        )
+    return out
+
+
+def face_centroid_device(vertices: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:
+    """connectivity.centroids (xugrid/ugrid/connectivity.py:636-664) on the device."""
+    L = _native.lib()
+    out = torch.empty((faces.shape[0], 2), dtype=torch.float64, device=faces.device)
+    with torch.cuda.device(faces.device):
+        _native.check(
+            L.xg_face_centroid(_native.ptr(vertices), _native.ptr(faces), faces.element_size(),
+                               int(faces.shape[0]), int(faces.shape[1]), _native.ptr(out),
+                               _native.stream_ptr())
+        )
+    return out

@@ -1,0 +1,440 @@
+// xg_index.cu -- packed, Morton-ordered mesh and wide BVH ("spatial index").
+//
+// Replaces numba_celltree.CellTree2d.__init__ as called from
+// /root/reference/xugrid/ugrid/ugrid2d.py:908-921 (bounding boxes + a bounding
+// interval hierarchy built serially on the CPU).  B200 design instead:
+//   1. one pass over the faces: vertex gather, bbox, 32-bit Morton key of the
+//      bbox centre                                              (k_face_keys)
+//   2. device radix sort of (key, face id)                      (cub)
+//   3. one pass in sorted order: gather again, force CCW, write the face as a
+//      self-contained record (bbox 32 B + vertices k*16 B)      (k_pack)
+//      -> later kernels never touch the indexed mesh again; neighbours in
+//      memory are neighbours in space, so a tile of queries reads contiguous
+//      runs that TMA/coalesced loads can stream
+//   4. FANOUT(32)-ary hierarchy over the sorted boxes, one warp per node,
+//      level by level: no atomics, no pointers, child j of node p at level l
+//      is entry 32*p + j of level l-1                           (k_reduce_level)
+#include <cub/device/device_radix_sort.cuh>
+
+#include "xg_common.cuh"
+#include "xg_pack.cuh"
+
+namespace xg {
+
+// ---- error plumbing ---------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e),
+              file, line, what);
+    return XG_ERR_CUDA;
+}
+
+// ---- kernels ------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long order_bits(double v) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double unorder_bits(unsigned long long u) {
+    u = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)u);
+#else
+    double d;
+    memcpy(&d, &u, 8);
+    return d;
+#endif
+}
+
+// red[0..3] = ordered bits of xmin, xmax, ymin, ymax over the nodes
+__global__ void k_node_bounds(const double2 *__restrict__ xy, int64_t n, unsigned long long *red) {
+    double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double2 p = xy[i];
+        xmin = fmin(xmin, p.x); xmax = fmax(xmax, p.x);
+        ymin = fmin(ymin, p.y); ymax = fmax(ymax, p.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(red + 0, order_bits(xmin));
+        atomicMax(red + 1, order_bits(xmax));
+        atomicMin(red + 2, order_bits(ymin));
+        atomicMax(red + 3, order_bits(ymax));
+    }
+}
+
+__global__ void k_init_red(unsigned long long *red) {
+    red[0] = ~0ull; red[1] = 0ull; red[2] = ~0ull; red[3] = 0ull; red[4] = 0ull;
+}
+
+// frame[0..3]: xmin, xmax, ymin, ymax used to quantise Morton keys (device memory)
+__global__ void k_frame_from_red(const unsigned long long *red, double *frame) {
+    frame[0] = unorder_bits(red[0]); frame[1] = unorder_bits(red[1]);
+    frame[2] = unorder_bits(red[2]); frame[3] = unorder_bits(red[3]);
+    frame[4] = sqrt(__longlong_as_double((long long)red[4])) * 1e-12;  // default tolerance
+}
+
+__device__ __forceinline__ uint32_t spread16(uint32_t v) {
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+template <typename I, int KMAX>
+__global__ void __launch_bounds__(256)
+k_face_keys(const double2 *__restrict__ xy, const I *__restrict__ faces, int64_t f_begin,
+            int64_t n, int k, const double *__restrict__ frame, uint32_t *__restrict__ keys,
+            int32_t *__restrict__ ids, unsigned long long *diag2_max) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double d2 = 0.0;
+    if (i < n) {
+        const I *face = faces + (f_begin + i) * k;
+        double2 p = xy[face[0]];
+        double xmin = p.x, xmax = p.x, ymin = p.y, ymax = p.y;
+#pragma unroll
+        for (int j = 1; j < KMAX; ++j) {
+            if (j >= k) break;
+            const I idx = face[j];
+            if (idx < 0) break;
+            p = xy[idx];
+            xmin = fmin(xmin, p.x); xmax = fmax(xmax, p.x);
+            ymin = fmin(ymin, p.y); ymax = fmax(ymax, p.y);
+        }
+        const double fx0 = frame[0], fx1 = frame[1], fy0 = frame[2], fy1 = frame[3];
+        const double cx = 0.5 * (xmin + xmax), cy = 0.5 * (ymin + ymax);
+        const double sx = fx1 > fx0 ? 65536.0 / (fx1 - fx0) : 0.0;
+        const double sy = fy1 > fy0 ? 65536.0 / (fy1 - fy0) : 0.0;
+        double qx = (cx - fx0) * sx, qy = (cy - fy0) * sy;
+        qx = fmin(fmax(qx, 0.0), 65535.0);
+        qy = fmin(fmax(qy, 0.0), 65535.0);
+        keys[i] = spread16((uint32_t)qx) | (spread16((uint32_t)qy) << 1);
+        ids[i] = (int32_t)(f_begin + i);
+        const double dx = xmax - xmin, dy = ymax - ymin;
+        d2 = dx * dx + dy * dy;
+    }
+    if (diag2_max) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+        if ((threadIdx.x & 31) == 0 && d2 > 0.0)
+            atomicMax(diag2_max, (unsigned long long)__double_as_longlong(d2));
+    }
+}
+
+// sorted position i <- face perm[i]: CCW-normalised vertices, bbox, vertex count
+template <typename I, int KMAX>
+__global__ void __launch_bounds__(256)
+k_pack(const double2 *__restrict__ xy, const I *__restrict__ faces, int k,
+       const int32_t *__restrict__ perm, int64_t n, Box *__restrict__ box,
+       double2 *__restrict__ poly, uint8_t *__restrict__ nvert) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const I *face = faces + (int64_t)perm[i] * k;
+    double2 v[KMAX];
+    int len = k;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+        if (j < k) {
+            const I idx = face[j];
+            if (idx < 0 && j >= 3 && len == k) len = j;  // first fill after a triangle ends it
+            v[j] = idx >= 0 ? xy[idx] : make_double2(0.0, 0.0);
+        }
+    }
+    // bounding box over the polygon (stops at the first fill value)
+    double xmin = v[0].x, xmax = v[0].x, ymin = v[0].y, ymax = v[0].y;
+#pragma unroll
+    for (int j = 1; j < KMAX; ++j)
+        if (j < len) {
+            xmin = fmin(xmin, v[j].x); xmax = fmax(xmax, v[j].x);
+            ymin = fmin(ymin, v[j].y); ymax = fmax(ymax, v[j].y);
+        }
+    // orientation: first non-collinear consecutive triple decides
+    bool flip = false;
+    {
+        double2 a = v[0], b = v[0];
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+            if (j == len - 2) a = v[j];
+            if (j == len - 1) b = v[j];
+        }
+        bool decided = false;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < len && !decided) {
+                const double2 c = v[j];
+                const double prod = (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x);
+                if (prod == 0.0) { a = b; b = c; }
+                else { flip = prod < 0.0; decided = true; }
+            }
+    }
+    double2 *dst = poly + i * k;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+        if (j < k) {
+            double2 o;
+            if (j < len) {
+                o = v[j];
+                if (flip) {
+#pragma unroll
+                    for (int q = 0; q < KMAX; ++q)
+                        if (q == len - 1 - j) o = v[q];
+                }
+            } else {
+                o = make_double2(0.0, 0.0);
+            }
+            dst[j] = o;
+        }
+    Box bx;
+    bx.xmin = xmin; bx.xmax = xmax; bx.ymin = ymin; bx.ymax = ymax;
+    box[i] = bx;
+    nvert[i] = (uint8_t)(len | (flip ? 0x80 : 0));
+}
+
+// one warp per parent: union of up to FANOUT child boxes
+__global__ void __launch_bounds__(256)
+k_reduce_level(const Box *__restrict__ child, int64_t n_child, Box *__restrict__ parent,
+               int64_t n_parent) {
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_parent) return;
+    const int64_t c = w * FANOUT + lane;
+    double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    if (c < n_child) {
+        const Box b = child[c];
+        xmin = b.xmin; xmax = b.xmax; ymin = b.ymin; ymax = b.ymax;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if (lane == 0) {
+        Box b;
+        b.xmin = xmin; b.xmax = xmax; b.ymin = ymin; b.ymax = ymax;
+        parent[w] = b;
+    }
+}
+
+// ---- host side ------------------------------------------------------------------
+template <typename I>
+static int launch_face_keys(const double2 *xy, const I *faces, int64_t f_begin, int64_t n, int k,
+                            const double *frame, uint32_t *keys, int32_t *ids,
+                            unsigned long long *diag2, cudaStream_t s) {
+    if (n == 0) return XG_OK;
+    const int B = 256;
+    const unsigned G = (unsigned)div_up(n, B);
+    if (k <= 3) k_face_keys<I, 3><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2);
+    else if (k <= 4) k_face_keys<I, 4><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2);
+    else k_face_keys<I, XG_MAX_N_VERTEX><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2);
+    XG_CHECK_LAUNCH();
+    return XG_OK;
+}
+
+template <typename I>
+static int launch_pack(const double2 *xy, const I *faces, int k, const int32_t *perm, int64_t n,
+                       Box *box, double2 *poly, uint8_t *nvert, cudaStream_t s) {
+    if (n == 0) return XG_OK;
+    const int B = 256;
+    const unsigned G = (unsigned)div_up(n, B);
+    if (k <= 3) k_pack<I, 3><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert);
+    else if (k <= 4) k_pack<I, 4><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert);
+    else if (k <= 8) k_pack<I, 8><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert);
+    else if (k <= 16) k_pack<I, 16><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert);
+    else k_pack<I, XG_MAX_N_VERTEX><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert);
+    XG_CHECK_LAUNCH();
+    return XG_OK;
+}
+
+static void ensure_pool_config() {
+    static bool done = false;
+    if (done) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;  // keep freed blocks cached: repeated builds reuse them
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done = true;
+}
+
+int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
+              int64_t f_end, int k, const double *d_frame, unsigned long long *d_diag2,
+              PackedMesh *out, cudaStream_t s) {
+    ensure_pool_config();
+    const int64_t n = f_end - f_begin;
+    out->n = n;
+    out->k = k;
+    const double2 *xy = reinterpret_cast<const double2 *>(d_xy);
+    DevBuf keys_in, keys_out, ids_in, tmp;
+    XG_CUDA(keys_in.alloc(sizeof(uint32_t) * (size_t)n, s));
+    XG_CUDA(keys_out.alloc(sizeof(uint32_t) * (size_t)n, s));
+    XG_CUDA(ids_in.alloc(sizeof(int32_t) * (size_t)n, s));
+    int rc;
+    if (idx_bytes == 4)
+        rc = launch_face_keys<int32_t>(xy, (const int32_t *)d_faces, f_begin, n, k, d_frame,
+                                       keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, s);
+    else
+        rc = launch_face_keys<int64_t>(xy, (const int64_t *)d_faces, f_begin, n, k, d_frame,
+                                       keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, s);
+    if (rc) return rc;
+    if (n > 0) {
+        size_t tb = 0;
+        XG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in.as<uint32_t>(),
+                                                keys_out.as<uint32_t>(), ids_in.as<int32_t>(),
+                                                out->perm, n, 0, 32, s));
+        XG_CUDA(tmp.alloc(tb, s));
+        XG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys_in.as<uint32_t>(),
+                                                keys_out.as<uint32_t>(), ids_in.as<int32_t>(),
+                                                out->perm, n, 0, 32, s));
+    }
+    if (idx_bytes == 4)
+        rc = launch_pack<int32_t>(xy, (const int32_t *)d_faces, k, out->perm, n, out->box,
+                                  reinterpret_cast<double2 *>(out->poly), out->nvert, s);
+    else
+        rc = launch_pack<int64_t>(xy, (const int64_t *)d_faces, k, out->perm, n, out->box,
+                                  reinterpret_cast<double2 *>(out->poly), out->nvert, s);
+    return rc;
+}
+
+}  // namespace xg
+
+using namespace xg;
+
+extern "C" int xg_abi_version(void) { return XG_ABI_VERSION; }
+extern "C" const char *xg_last_error_string(void) { return xg::g_err; }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int xg_index_create(const double *d_xy, int64_t n_node, const void *d_faces,
+                               int idx_bytes, int64_t n_face, int k, void *stream,
+                               xg_index **out) {
+    if (!out) { set_error("xg_index_create: out is NULL"); return XG_ERR_INVALID; }
+    *out = nullptr;
+    if (n_face < 0 || n_node < 0 || (idx_bytes != 4 && idx_bytes != 8) ||
+        (n_face > 0 && (!d_xy || !d_faces))) {
+        set_error("xg_index_create: invalid argument");
+        return XG_ERR_INVALID;
+    }
+    if (k < 3 || k > XG_MAX_N_VERTEX) {
+        set_error("xg_index_create: faces must have 3..%d vertices, got %d", XG_MAX_N_VERTEX, k);
+        return XG_ERR_UNSUPPORTED;
+    }
+    if (n_face >= (int64_t)1 << 31) {
+        set_error("xg_index_create: more than 2^31 faces");
+        return XG_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    ensure_pool_config();
+    xg_index *ix = new xg_index();
+    ix->n_face = n_face; ix->n_node = n_node; ix->k = k;
+
+    // level sizes
+    int64_t level_n[MAX_LEVELS];
+    int n_levels = 0;
+    int64_t cur = n_face;
+    while (n_face > 0 && n_levels < MAX_LEVELS) {
+        cur = div_up(cur, FANOUT);
+        level_n[n_levels++] = cur;
+        if (cur <= FANOUT) break;
+    }
+    ix->n_levels = n_levels;
+
+    // one arena: boxes | level boxes | poly | perm | nvert | frame(8 doubles) | red(8 u64)
+    size_t off = 0;
+    const size_t off_box = off; off = align_up(off + sizeof(Box) * (size_t)n_face, 256);
+    size_t off_lvl[MAX_LEVELS];
+    for (int l = 0; l < n_levels; ++l) {
+        off_lvl[l] = off;
+        off = align_up(off + sizeof(Box) * (size_t)level_n[l], 256);
+    }
+    const size_t off_poly = off; off = align_up(off + sizeof(double) * 2 * (size_t)k * (size_t)n_face, 256);
+    const size_t off_perm = off; off = align_up(off + sizeof(int32_t) * (size_t)n_face, 256);
+    const size_t off_nv = off; off = align_up(off + (size_t)n_face, 256);
+    const size_t off_frame = off; off = align_up(off + sizeof(double) * 8, 256);
+    const size_t off_red = off; off = align_up(off + sizeof(unsigned long long) * 8, 256);
+    ix->bytes = off;
+    cudaError_t e = cudaMallocAsync(&ix->arena, off, s);
+    if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMallocAsync(index)", __FILE__, __LINE__); }
+    char *base = (char *)ix->arena;
+    ix->leaf_box = (Box *)(base + off_box);
+    for (int l = 0; l < n_levels; ++l) { ix->level_box[l] = (Box *)(base + off_lvl[l]); ix->level_n[l] = level_n[l]; }
+    ix->poly = (double *)(base + off_poly);
+    ix->perm = (int32_t *)(base + off_perm);
+    ix->nvert = (uint8_t *)(base + off_nv);
+    double *d_frame = (double *)(base + off_frame);
+    ix->d_frame = d_frame;
+    unsigned long long *d_red = (unsigned long long *)(base + off_red);
+
+    int rc = XG_OK;
+    do {
+        k_init_red<<<1, 1, 0, s>>>(d_red);
+        if (n_node > 0)
+            k_node_bounds<<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)d_xy, n_node, d_red);
+        k_frame_from_red<<<1, 1, 0, s>>>(d_red, d_frame);
+        if (cudaGetLastError() != cudaSuccess) { rc = XG_ERR_CUDA; set_error("index: launch failed"); break; }
+        PackedMesh pm;
+        pm.perm = ix->perm; pm.box = ix->leaf_box; pm.poly = ix->poly; pm.nvert = ix->nvert;
+        rc = pack_mesh(d_xy, d_faces, idx_bytes, 0, n_face, k, d_frame, d_red + 4, &pm, s);
+        if (rc) break;
+        // tolerance needs the max diagonal, which k_face_keys has now reduced
+        k_frame_from_red<<<1, 1, 0, s>>>(d_red, d_frame);
+        const Box *child = ix->leaf_box;
+        int64_t n_child = n_face;
+        for (int l = 0; l < n_levels; ++l) {
+            const int64_t np = level_n[l];
+            k_reduce_level<<<(unsigned)div_up(np * 32, 256), 256, 0, s>>>(child, n_child, ix->level_box[l], np);
+            child = ix->level_box[l];
+            n_child = np;
+        }
+        if (cudaGetLastError() != cudaSuccess) { rc = XG_ERR_CUDA; set_error("index: launch failed"); break; }
+        double h[5];
+        e = cudaMemcpyAsync(h, d_frame, sizeof(h), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "index finalize", __FILE__, __LINE__); break; }
+        ix->bounds[0] = h[0]; ix->bounds[1] = h[1]; ix->bounds[2] = h[2]; ix->bounds[3] = h[3];
+        ix->default_tolerance = h[4];
+    } while (0);
+    if (rc) {
+        cudaFreeAsync(ix->arena, s);
+        delete ix;
+        return rc;
+    }
+    *out = ix;
+    return XG_OK;
+}
+
+extern "C" int xg_index_destroy(xg_index *ix) {
+    if (!ix) return XG_OK;
+    if (ix->arena) cudaFree(ix->arena);
+    delete ix;
+    return XG_OK;
+}
+
+extern "C" int xg_index_info(const xg_index *ix, int64_t info[8], double *tol) {
+    if (!ix) { set_error("xg_index_info: NULL index"); return XG_ERR_INVALID; }
+    if (info) {
+        info[0] = ix->n_face; info[1] = ix->k; info[2] = ix->n_levels; info[3] = (int64_t)ix->bytes;
+        info[4] = ix->n_node; info[5] = info[6] = info[7] = 0;
+    }
+    if (tol) *tol = ix->default_tolerance;
+    return XG_OK;
+}

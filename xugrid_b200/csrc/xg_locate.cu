@@ -1,0 +1,238 @@
+// xg_locate.cu -- point location and barycentric weights.
+//
+// Replaces CellTree2d.locate_points / compute_barycentric_weights as called from
+// /root/reference/xugrid/regrid/unstructured.py:138-139,
+// /root/reference/xugrid/ugrid/ugridbase.py:1305-1323 and
+// /root/reference/xugrid/ugrid/ugrid2d.py:1054-1078,1099.
+//
+// Points are Morton-sorted (same frame as the index) so that a warp owns 32
+// neighbouring points and walks the wide BVH once for all of them (lane =
+// point), exactly like the face tiles of xg_overlap.cu.  A face qualifies when
+// the point is inside by ray casting or within `tolerance` of one of its
+// edges; boxes are therefore tested with a margin of 1.5 * tolerance (a point
+// that passes the on-edge test lies within sqrt(2) * tolerance of the face).
+// Among qualifying faces the smallest caller face id wins, which makes the
+// answer independent of the tree.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "xg_common.cuh"
+#include "xg_geom.cuh"
+
+namespace xg {
+
+constexpr int LOC_WARPS = 8;
+constexpr int LOC_STACK = 256;
+
+struct LocateParams {
+    const Box *boxes[MAX_LEVELS + 1];
+    int64_t count[MAX_LEVELS + 1];
+    int top;
+};
+
+__device__ __forceinline__ uint32_t spread16p(uint32_t v) {
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+k_point_keys(const double2 *__restrict__ pts, int64_t n, const double *__restrict__ frame,
+             uint32_t *__restrict__ keys, int32_t *__restrict__ ids) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 p = pts[i];
+    const double fx0 = frame[0], fx1 = frame[1], fy0 = frame[2], fy1 = frame[3];
+    const double sx = fx1 > fx0 ? 65536.0 / (fx1 - fx0) : 0.0;
+    const double sy = fy1 > fy0 ? 65536.0 / (fy1 - fy0) : 0.0;
+    double qx = (p.x - fx0) * sx, qy = (p.y - fy0) * sy;
+    // NaN-safe clamp: fmax(NaN, 0) = 0
+    qx = fmin(fmax(qx, 0.0), 65535.0);
+    qy = fmin(fmax(qy, 0.0), 65535.0);
+    keys[i] = spread16p((uint32_t)qx) | (spread16p((uint32_t)qy) << 1);
+    ids[i] = (int32_t)i;
+}
+
+__device__ __forceinline__ bool point_in_box(double px, double py, const Box &b, double m) {
+    return px >= b.xmin - m && px <= b.xmax + m && py >= b.ymin - m && py <= b.ymax + m;
+}
+
+// lane = point (Morton order).  Writes the caller's face id (or -1) at the
+// point's original position, and the face's sorted position in pos_out.
+__global__ void __launch_bounds__(LOC_WARPS * 32)
+k_locate(const LocateParams P, const double2 *__restrict__ pts, const int32_t *__restrict__ order,
+         int64_t n, const double2 *__restrict__ poly, const uint8_t *__restrict__ nvert, int k,
+         const int32_t *__restrict__ perm, double tol, int32_t *__restrict__ face_out,
+         int32_t *__restrict__ pos_out) {
+    __shared__ Box s_node[LOC_WARPS][32];
+    __shared__ int32_t s_stack[LOC_WARPS][LOC_STACK];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = blockIdx.x * (int64_t)LOC_WARPS + w;
+    const int64_t i = tile * 32 + lane;
+    if (tile * 32 >= n) return;
+    const bool valid = i < n;
+    const int32_t orig = valid ? order[i] : -1;
+    double px = NAN, py = NAN;
+    if (valid) { const double2 p = pts[orig]; px = p.x; py = p.y; }
+    const double margin = 1.5 * tol;
+    const double tol2 = tol * tol;
+    // union box of the tile's points (NaN points never match anything)
+    Box ub;
+    ub.xmin = valid && px == px ? px : INFINITY; ub.xmax = valid && px == px ? px : -INFINITY;
+    ub.ymin = valid && py == py ? py : INFINITY; ub.ymax = valid && py == py ? py : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ub.xmin = fmin(ub.xmin, __shfl_xor_sync(0xffffffffu, ub.xmin, o));
+        ub.xmax = fmax(ub.xmax, __shfl_xor_sync(0xffffffffu, ub.xmax, o));
+        ub.ymin = fmin(ub.ymin, __shfl_xor_sync(0xffffffffu, ub.ymin, o));
+        ub.ymax = fmax(ub.ymax, __shfl_xor_sync(0xffffffffu, ub.ymax, o));
+    }
+    int32_t best = 0x7fffffff, best_pos = -1;
+    int sp = 1;
+    if (lane == 0) s_stack[w][0] = P.top << 27;
+    __syncwarp();
+    while (sp > 0) {
+        const int32_t entry = s_stack[w][--sp];
+        const int d = entry >> 27;
+        const int64_t c0 = (int64_t)(entry & 0x7ffffff) * FANOUT;
+        const Box *cb = P.boxes[d - 1];
+        const int64_t nc = P.count[d - 1] - c0;
+        Box mine;
+        if (lane < nc) mine = cb[c0 + lane];
+        else { mine.xmin = INFINITY; mine.xmax = -INFINITY; mine.ymin = INFINITY; mine.ymax = -INFINITY; }
+        const bool pre = mine.xmin - margin <= ub.xmax && ub.xmin <= mine.xmax + margin &&
+                         mine.ymin - margin <= ub.ymax && ub.ymin <= mine.ymax + margin;
+        unsigned m = __ballot_sync(0xffffffffu, pre);
+        __syncwarp();
+        if (m == 0) continue;
+        s_node[w][lane] = mine;
+        __syncwarp();
+        if (d > 1) {
+            while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                const Box b = s_node[w][c];
+                if (__any_sync(0xffffffffu, point_in_box(px, py, b, margin))) {
+                    if (lane == 0) s_stack[w][sp] = ((d - 1) << 27) | (int32_t)(c0 + c);
+                    ++sp;
+                }
+            }
+        } else {
+            while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                const Box b = s_node[w][c];
+                if (point_in_box(px, py, b, margin)) {
+                    const int64_t pos = c0 + c;
+                    const int32_t fid = perm[pos];
+                    if (fid < best &&
+                        point_in_polygon_or_on_edge(px, py, poly + pos * k, nvert[pos] & 0x7f, tol2)) {
+                        best = fid;
+                        best_pos = (int32_t)pos;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (valid) {
+        face_out[orig] = best_pos >= 0 ? best : -1;
+        if (pos_out) pos_out[orig] = best_pos;
+    }
+}
+
+// one thread per point: weights for the vertices of the located face, written
+// in the caller's vertex order (a face that was flipped to CCW is un-flipped)
+__global__ void __launch_bounds__(128)
+k_barycentric(const double2 *__restrict__ pts, int64_t n, const int32_t *__restrict__ pos_in,
+              const double2 *__restrict__ poly, const uint8_t *__restrict__ nvert, int k, double tol,
+              double *__restrict__ weights) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double *wout = weights + i * k;
+    for (int j = 0; j < k; ++j) wout[j] = 0.0;
+    const int32_t pos = pos_in[i];
+    if (pos < 0) return;
+    const double2 p = pts[i];
+    const double2 *pg = poly + (int64_t)pos * k;
+    const uint8_t nvf = nvert[pos];
+    const int len = nvf & 0x7f;
+    const bool flip = nvf & 0x80;
+    double w[XG_MAX_N_VERTEX];
+    if (k == 3) bary_triangle(pg, p.x, p.y, w);
+    else bary_wachspress(pg, len, p.x, p.y, tol * tol, w);
+    for (int j = 0; j < len; ++j) wout[flip ? len - 1 - j : j] = w[j];
+}
+
+static int locate_impl(const xg_index *ix, const double *d_points, int64_t n, double tol,
+                       int32_t *d_face, int32_t *d_pos, cudaStream_t s) {
+    if (n == 0) return XG_OK;
+    if (ix->n_face == 0) {
+        XG_CUDA(cudaMemsetAsync(d_face, 0xff, sizeof(int32_t) * (size_t)n, s));
+        if (d_pos) XG_CUDA(cudaMemsetAsync(d_pos, 0xff, sizeof(int32_t) * (size_t)n, s));
+        return XG_OK;
+    }
+    DevBuf keys_in, keys_out, ids_in, order, tmp;
+    XG_CUDA(keys_in.alloc(sizeof(uint32_t) * (size_t)n, s));
+    XG_CUDA(keys_out.alloc(sizeof(uint32_t) * (size_t)n, s));
+    XG_CUDA(ids_in.alloc(sizeof(int32_t) * (size_t)n, s));
+    XG_CUDA(order.alloc(sizeof(int32_t) * (size_t)n, s));
+    k_point_keys<<<(unsigned)div_up(n, 256), 256, 0, s>>>((const double2 *)d_points, n, ix->d_frame,
+                                                         keys_in.as<uint32_t>(), ids_in.as<int32_t>());
+    XG_CHECK_LAUNCH();
+    size_t tb = 0;
+    XG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in.as<uint32_t>(), keys_out.as<uint32_t>(),
+                                            ids_in.as<int32_t>(), order.as<int32_t>(), n, 0, 32, s));
+    XG_CUDA(tmp.alloc(tb, s));
+    XG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys_in.as<uint32_t>(), keys_out.as<uint32_t>(),
+                                            ids_in.as<int32_t>(), order.as<int32_t>(), n, 0, 32, s));
+    LocateParams P;
+    P.boxes[0] = ix->leaf_box; P.count[0] = ix->n_face;
+    for (int l = 0; l < ix->n_levels; ++l) { P.boxes[l + 1] = ix->level_box[l]; P.count[l + 1] = ix->level_n[l]; }
+    P.top = ix->n_levels + 1;
+    const unsigned tiles = (unsigned)div_up(n, 32);
+    k_locate<<<(unsigned)div_up(tiles, LOC_WARPS), LOC_WARPS * 32, 0, s>>>(
+        P, (const double2 *)d_points, order.as<int32_t>(), n, (const double2 *)ix->poly, ix->nvert,
+        ix->k, ix->perm, tol, d_face, d_pos);
+    XG_CHECK_LAUNCH();
+    return XG_OK;
+}
+
+}  // namespace xg
+
+using namespace xg;
+
+extern "C" int xg_locate_points(const xg_index *index, const double *d_points, int64_t n_point,
+                                double tolerance, int32_t *d_face_index, void *stream) {
+    if (!index || n_point < 0 || (n_point > 0 && (!d_points || !d_face_index))) {
+        set_error("xg_locate_points: invalid argument");
+        return XG_ERR_INVALID;
+    }
+    if (n_point >= (int64_t)1 << 31) { set_error("xg_locate_points: more than 2^31 points"); return XG_ERR_UNSUPPORTED; }
+    const double tol = tolerance < 0 ? index->default_tolerance : tolerance;
+    return locate_impl(index, d_points, n_point, tol, d_face_index, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int xg_barycentric(const xg_index *index, const double *d_points, int64_t n_point,
+                              double tolerance, int32_t *d_face_index, double *d_weights,
+                              void *stream) {
+    if (!index || n_point < 0 || (n_point > 0 && (!d_points || !d_face_index || !d_weights))) {
+        set_error("xg_barycentric: invalid argument");
+        return XG_ERR_INVALID;
+    }
+    if (n_point >= (int64_t)1 << 31) { set_error("xg_barycentric: more than 2^31 points"); return XG_ERR_UNSUPPORTED; }
+    if (n_point == 0) return XG_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const double tol = tolerance < 0 ? index->default_tolerance : tolerance;
+    DevBuf pos;
+    XG_CUDA(pos.alloc(sizeof(int32_t) * (size_t)n_point, s));
+    int rc = locate_impl(index, d_points, n_point, tol, d_face_index, pos.as<int32_t>(), s);
+    if (rc) return rc;
+    k_barycentric<<<(unsigned)div_up(n_point, 128), 128, 0, s>>>(
+        (const double2 *)d_points, n_point, pos.as<int32_t>(), (const double2 *)index->poly,
+        index->nvert, index->k, tol, d_weights);
+    XG_CHECK_LAUNCH();
+    return XG_OK;
+}

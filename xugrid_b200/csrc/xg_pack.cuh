@@ -1,0 +1,24 @@
+// xg_pack.cuh -- a mesh range repacked in Morton order (see xg_index.cu).
+#pragma once
+#include "xg_common.cuh"
+
+namespace xg {
+
+// Output arrays are caller-allocated device memory of n = f_end - f_begin
+// entries (poly: n * k * 2 doubles).
+struct PackedMesh {
+    int64_t n = 0;
+    int k = 0;
+    int32_t *perm = nullptr;   // sorted position -> caller's face id (absolute)
+    Box *box = nullptr;        // bbox per sorted face
+    double *poly = nullptr;    // (n, k, 2) CCW vertices per sorted face
+    uint8_t *nvert = nullptr;  // vertex count | 0x80 if the face was flipped
+};
+
+// d_frame: device pointer to [xmin, xmax, ymin, ymax] used to quantise the
+// Morton keys; d_diag2 (optional): running max of squared bbox diagonals.
+int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
+              int64_t f_end, int k, const double *d_frame, unsigned long long *d_diag2,
+              PackedMesh *out, cudaStream_t s);
+
+}  // namespace xg

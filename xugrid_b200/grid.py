@@ -1,0 +1,322 @@
+"""
+Minimal mesh containers for the regridding path.
+
+``Ugrid2d`` keeps only what the hot path of xugrid's class of the same name
+touches (/root/reference/xugrid/ugrid/ugrid2d.py:87-109 constructor
+normalisation, ``node_coordinates`` ugridbase.py:576-579, ``centroids``
+ugrid2d.py:544-559, ``area`` :575-584, ``celltree`` :908-921,
+``locate_points`` ugridbase.py:1305-1323, ``compute_barycentric_weights``
+ugrid2d.py:1054-1078, ``rasterize_like`` :1080-1101,
+``from_structured_bounds`` :1973-2034).  Geometry is evaluated on the GPU.
+
+``StructuredGrid2d`` covers only the promotion of a raster to a quad mesh
+(/root/reference/xugrid/regrid/structured.py:24-100,489-501); the separable
+structured-to-structured path of the reference is out of scope and such pairs
+are regridded as quad meshes.
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from .celltree import CellTree2d, face_area_device, face_centroid_device, faces_to_device, to_device
+
+FILL_VALUE = -1
+
+
+class Ugrid2d:
+    def __init__(self, node_x, node_y, fill_value: int, face_node_connectivity,
+                 name: str = "mesh2d", start_index: int = 0, device=None):
+        self.node_x = np.ascontiguousarray(_host(node_x), dtype=np.float64)
+        self.node_y = np.ascontiguousarray(_host(node_y), dtype=np.float64)
+        if self.node_x.ndim != 1 or self.node_x.shape != self.node_y.shape:
+            raise ValueError("node_x and node_y must be 1D arrays of equal length")
+        if not isinstance(face_node_connectivity, (np.ndarray, torch.Tensor)):
+            raise TypeError(
+                "face_node_connectivity should be an array of integers or a sparse matrix"
+            )
+        conn = np.array(_host(face_node_connectivity), copy=True)
+        if conn.dtype not in (np.int32, np.int64):
+            conn = conn.astype(np.int64)
+        if conn.ndim != 2:
+            raise ValueError("face_node_connectivity must be (n_face, n_max_node)")
+        # ugrid2d.py:103-109: fill value -> -1, indices 0-based
+        if fill_value != FILL_VALUE or start_index != 0:
+            is_fill = conn == fill_value
+            if start_index != 0:
+                conn[~is_fill] -= start_index
+            if fill_value != FILL_VALUE:
+                conn[is_fill] = FILL_VALUE
+        self.face_node_connectivity = conn
+        self.fill_value = FILL_VALUE
+        self.start_index = 0
+        self.name = name
+        self.device = device
+        self._clear()
+
+    def _clear(self):
+        self._celltree = None
+        self._xy_d = None
+        self._faces_d = None
+        self._centroids = None
+        self._area = None
+
+    # ---- basic properties -------------------------------------------------------
+    @property
+    def n_node(self) -> int:
+        return self.node_x.size
+
+    @property
+    def n_face(self) -> int:
+        return self.face_node_connectivity.shape[0]
+
+    @property
+    def n_max_node_per_face(self) -> int:
+        return self.face_node_connectivity.shape[1]
+
+    @property
+    def face_dimension(self) -> str:
+        return f"{self.name}_nFaces"
+
+    @property
+    def core_dimension(self) -> str:
+        return self.face_dimension
+
+    @property
+    def node_coordinates(self) -> np.ndarray:
+        return np.column_stack([self.node_x, self.node_y])
+
+    @property
+    def bounds(self) -> Tuple[float, float, float, float]:
+        return (float(self.node_x.min()), float(self.node_y.min()),
+                float(self.node_x.max()), float(self.node_y.max()))
+
+    # ---- device mirrors ------------------------------------------------------------
+    def _dev(self) -> torch.device:
+        if self.device is None:
+            return torch.device("cuda", torch.cuda.current_device())
+        return torch.device(self.device)
+
+    def device_arrays(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(n_node, 2) float64 and (n_face, k) int tensors in HBM (cached)."""
+        if self._xy_d is None:
+            dev = self._dev()
+            self._xy_d = to_device(self.node_coordinates, torch.float64, dev)
+            self._faces_d = faces_to_device(self.face_node_connectivity, FILL_VALUE, dev)
+        return self._xy_d, self._faces_d
+
+    @property
+    def celltree(self) -> CellTree2d:
+        if self._celltree is None:
+            xy, faces = self.device_arrays()
+            self._celltree = CellTree2d(xy, faces, FILL_VALUE, device=self._dev())
+        return self._celltree
+
+    @property
+    def centroids_device(self) -> torch.Tensor:
+        xy, faces = self.device_arrays()
+        return face_centroid_device(xy, faces)
+
+    @property
+    def centroids(self) -> np.ndarray:
+        if self._centroids is None:
+            self._centroids = self.centroids_device.cpu().numpy()
+        return self._centroids
+
+    @property
+    def area_device(self) -> torch.Tensor:
+        xy, faces = self.device_arrays()
+        return face_area_device(xy, faces)
+
+    @property
+    def area(self) -> np.ndarray:
+        if self._area is None:
+            self._area = self.area_device.cpu().numpy()
+        return self._area
+
+    # ---- queries ----------------------------------------------------------------------
+    def locate_points(self, points, tolerance: Optional[float] = None) -> np.ndarray:
+        return self.celltree.locate_points(points, tolerance)
+
+    def compute_barycentric_weights(self, points, tolerance: Optional[float] = None):
+        return self.celltree.compute_barycentric_weights(points, tolerance)
+
+    def rasterize_like(self, x, y):
+        # ugrid2d.py:1080-1101
+        x = np.asarray(x, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        yy, xx = np.meshgrid(y, x, indexing="ij")
+        nodes = np.column_stack([xx.ravel(), yy.ravel()])
+        index = self.celltree.locate_points(nodes).reshape((y.size, x.size))
+        return x, y, index
+
+    def rasterize(self, resolution: float, bounds=None):
+        # ugrid2d.py:1103-1136
+        if bounds is None:
+            bounds = self.bounds
+        xmin, ymin, xmax, ymax = bounds
+        d = abs(resolution)
+        xmin = np.floor(xmin / d) * d
+        xmax = np.ceil(xmax / d) * d
+        ymin = np.floor(ymin / d) * d
+        ymax = np.ceil(ymax / d) * d
+        x = np.arange(xmin + 0.5 * d, xmax, d)
+        y = np.arange(ymax - 0.5 * d, ymin, -d)
+        return self.rasterize_like(x, y)
+
+    # ---- constructors -------------------------------------------------------------------
+    @staticmethod
+    def _from_intervals_helper(node_x, node_y, nx: int, ny: int, name: str) -> "Ugrid2d":
+        # ugrid2d.py:1894-1912: counter-clockwise quads over a node lattice
+        linear_index = np.arange(node_x.size, dtype=np.int64).reshape((ny + 1, nx + 1))
+        face_nodes = np.empty((ny * nx, 4), dtype=np.int64)
+        left, right = slice(None, -1), slice(1, None)
+        lower, upper = slice(None, -1), slice(1, None)
+        if node_x[1] < node_x[0]:
+            left, right = right, left
+        if node_y[nx + 1] < node_y[0]:
+            lower, upper = upper, lower
+        face_nodes[:, 0] = linear_index[lower, left].ravel()
+        face_nodes[:, 1] = linear_index[lower, right].ravel()
+        face_nodes[:, 2] = linear_index[upper, right].ravel()
+        face_nodes[:, 3] = linear_index[upper, left].ravel()
+        return Ugrid2d(node_x, node_y, -1, face_nodes, name=name)
+
+    @staticmethod
+    def from_structured_bounds(x_bounds, y_bounds, name: str = "mesh2d") -> "Ugrid2d":
+        # ugrid2d.py:1973-2034 (2D bounds only)
+        x_bounds = np.asarray(x_bounds, dtype=np.float64)
+        y_bounds = np.asarray(y_bounds, dtype=np.float64)
+        if x_bounds.ndim != 2 or y_bounds.ndim != 2:
+            raise ValueError(f"Expected 2 dimensions on bounds, received: {x_bounds.ndim}")
+        nx, ny = x_bounds.shape[0], y_bounds.shape[0]
+        x = bounds1d_to_vertices(x_bounds)
+        y = bounds1d_to_vertices(y_bounds)
+        node_y, node_x = (a.ravel() for a in np.meshgrid(y, x, indexing="ij"))
+        return Ugrid2d._from_intervals_helper(node_x, node_y, nx, ny, name)
+
+
+def _host(a):
+    if isinstance(a, torch.Tensor):
+        return a.detach().cpu().numpy()
+    return np.asarray(a)
+
+
+def bounds1d_to_vertices(bounds: np.ndarray) -> np.ndarray:
+    # /root/reference/xugrid/conversion.py:272-282
+    diff = np.diff(bounds, axis=0)
+    ascending = (diff >= 0.0).all()
+    descending = (diff <= 0.0).all()
+    if ascending:
+        return np.concatenate((bounds[:, 0], bounds[-1:, 1]))
+    elif descending:
+        return np.concatenate((bounds[:, 1], bounds[-1:, 0]))
+    raise ValueError("Bounds are not monotonic ascending or monotonic descending")
+
+
+class StructuredAxis:
+    """One raster axis: midpoints -> cell bounds (structured.py:24-100)."""
+
+    def __init__(self, midpoints, name: str, bounds=None, size=None):
+        index = np.asarray(midpoints, dtype=np.float64)
+        if index.ndim != 1 or index.size < 1:
+            raise ValueError(f"{name} must be a 1D coordinate")
+        d = np.diff(index)
+        if index.size > 1 and (d < 0).all():
+            mid = index[::-1]
+            self.flipped = True
+        elif index.size == 1 or (d > 0).all():
+            mid = index
+            self.flipped = False
+        else:
+            raise ValueError(f"{name} is not monotonic")
+        if bounds is not None:
+            b = np.asarray(bounds, dtype=np.float64)
+        else:
+            if size is None:
+                if mid.size < 2:
+                    raise ValueError(f"cannot infer the cell size of {name} from one midpoint")
+                size = np.diff(mid)
+                atolx = 1.0e-4 * size[0]
+                if not np.allclose(size, size[0], atolx):
+                    raise ValueError(
+                        f"DataArray has to be equidistant along {name}, or "
+                        f'explicit bounds must be given as "{name}bounds", or '
+                        f'cellsizes must be as "d{name}"'
+                    )
+                size = np.full_like(mid, size[0])
+            abs_size = np.abs(np.broadcast_to(np.asarray(size, dtype=np.float64), mid.shape))
+            b = np.column_stack((mid - 0.5 * abs_size, mid + 0.5 * abs_size))
+        self.name = name
+        self.index = index
+        self.midpoints = mid
+        self.bounds = b
+
+    @property
+    def size(self) -> int:
+        return len(self.bounds)
+
+    @property
+    def directional_bounds(self) -> np.ndarray:
+        return self.bounds[::-1, :].copy() if self.flipped else self.bounds
+
+
+class StructuredGrid2d:
+    """A raster given by its x and y cell midpoints (or explicit bounds)."""
+
+    def __init__(self, x, y, xbounds=None, ybounds=None, name_x: str = "x", name_y: str = "y"):
+        self.xbounds = StructuredAxis(x, name_x, xbounds)
+        self.ybounds = StructuredAxis(y, name_y, ybounds)
+
+    @property
+    def ndim(self) -> int:
+        return 2
+
+    @property
+    def dims(self) -> Tuple[str, str]:
+        return (self.ybounds.name, self.xbounds.name)
+
+    @property
+    def shape(self) -> Tuple[int, int]:
+        return (self.ybounds.size, self.xbounds.size)
+
+    @property
+    def size(self) -> int:
+        return self.ybounds.size * self.xbounds.size
+
+    @property
+    def coords(self) -> dict:
+        return {self.ybounds.name: self.ybounds.index, self.xbounds.name: self.xbounds.index}
+
+    def to_ugrid2d(self) -> Ugrid2d:
+        # structured.py:489-501
+        return Ugrid2d.from_structured_bounds(
+            self.xbounds.directional_bounds, self.ybounds.directional_bounds
+        )
+
+
+class UgridDataArray:
+    """Face data on a mesh: the small part of xugrid.UgridDataArray the
+    regridders need (values whose LAST axis is the face dimension)."""
+
+    def __init__(self, data, grid: Ugrid2d, dims: Optional[Tuple[str, ...]] = None):
+        self.data = data
+        self.grid = grid
+        nd = data.ndim if hasattr(data, "ndim") else np.ndim(data)
+        if data.shape[-1] != grid.n_face:
+            raise ValueError("last axis of data must be the face dimension")
+        self.dims = tuple(dims) if dims is not None else tuple(
+            [f"dim_{i}" for i in range(nd - 1)] + [grid.face_dimension]
+        )
+
+    @property
+    def values(self):
+        d = self.data
+        return d.cpu().numpy() if isinstance(d, torch.Tensor) else np.asarray(d)
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)

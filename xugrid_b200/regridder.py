@@ -1,0 +1,396 @@
+"""
+The regridder classes of xugrid.regrid with the same constructor / ``regrid`` /
+``weights`` / ``from_weights`` / ``from_dataset`` surface
+(/root/reference/xugrid/regrid/regridder.py:99-659), computing on a B200
+through libxgregrid.so.
+
+Differences that follow from running on a GPU without xarray:
+
+* data goes in as ``UgridDataArray`` (xugrid_b200.grid), numpy array or torch
+  tensor whose trailing axes are the source grid's; the same kind comes back.
+* ``method`` is a name from reduce.py or the object returned by
+  ``OverlapRegridder.create_percentile_method(p)``; arbitrary Python callables
+  (numba-compiled by the reference, regridder.py:135-136) raise
+  ``NotImplementedError``.
+* ``weights`` / ``to_dataset()`` return a plain ``dict`` of numpy arrays with
+  the reference's variable names (``__regrid_data`` ...,
+  regridder.py:264-271); ``from_weights`` / ``from_dataset`` read it back.
+* a ``target_range=(begin, end)`` keyword builds and applies only a contiguous
+  range of target faces (one shard per GPU; see xugrid_b200.distributed).
+"""
+
+from __future__ import annotations
+
+import abc
+from typing import Callable, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import sparse
+from .grid import StructuredGrid2d, Ugrid2d, UgridDataArray
+from .sparse import MatrixCOO, MatrixCSR
+
+
+class PercentileMethod:
+    """Returned by create_percentile_method (reduce.py:241-248)."""
+
+    def __init__(self, p: float):
+        if not (0.0 <= p <= 100.0):
+            raise ValueError(f"percentile must be in the range [0, 100], received: {p}")
+        self.percentile = float(p)
+
+    def __call__(self, values, weights, workspace=None):  # host evaluation for inspection only
+        raise NotImplementedError("percentile methods are evaluated on the GPU")
+
+
+def create_percentile_method(p: float) -> PercentileMethod:
+    return PercentileMethod(p)
+
+
+ABSOLUTE_OVERLAP_METHODS = (
+    "mean", "harmonic_mean", "geometric_mean", "sum", "minimum", "maximum", "mode", "median",
+    "max_overlap", "p5", "p10", "p25", "p50", "p75", "p90", "p95",
+)
+RELATIVE_OVERLAP_METHODS = ("conductance", "first_order_conservative")
+
+
+class UnstructuredGrid2d:
+    """Topology adapter (/root/reference/xugrid/regrid/unstructured.py:60-220)."""
+
+    def __init__(self, obj):
+        if isinstance(obj, UgridDataArray):
+            self.ugrid_topology = obj.grid
+        elif isinstance(obj, Ugrid2d):
+            self.ugrid_topology = obj
+        else:
+            options = {"Ugrid2d", "UgridDataArray", "UgridDataset"}
+            raise TypeError(f"Expected one of {options}, received: {type(obj).__name__}")
+
+    ndim = 1
+
+    @property
+    def dims(self):
+        return (self.ugrid_topology.face_dimension,)
+
+    @property
+    def shape(self):
+        return (self.ugrid_topology.n_face,)
+
+    @property
+    def size(self):
+        return self.ugrid_topology.n_face
+
+    @property
+    def area(self):
+        return self.ugrid_topology.area
+
+    def to_unstructured(self) -> "UnstructuredGrid2d":
+        return self
+
+    def overlap(self, other: "UnstructuredGrid2d", relative: bool,
+                target_range: Optional[Tuple[int, int]] = None) -> MatrixCSR:
+        """unstructured.py:109-135 + sparse.py:119-127, as one device CSR."""
+        tree = self.ugrid_topology.celltree
+        xy, faces = other.ugrid_topology.device_arrays()
+        t_begin, t_end = (0, other.size) if target_range is None else target_range
+        indptr, indices, data = tree.intersect_faces_csr(
+            xy, faces, -1, t_begin=t_begin, t_end=t_end, relative=relative
+        )
+        return MatrixCSR(data, indices, indptr, t_end - t_begin, self.size, int(data.numel()))
+
+    def locate_centroids(self, other: "UnstructuredGrid2d", tolerance: Optional[float] = None):
+        """unstructured.py:137-144: (source_index, target_index, ones) device tensors."""
+        tree = self.ugrid_topology.celltree
+        idx = tree.locate_points_device(other.ugrid_topology.centroids_device, tolerance)
+        inside = idx != -1
+        source_index = idx[inside]
+        target_index = torch.arange(other.size, dtype=torch.int32, device=idx.device)[inside]
+        weights = torch.ones(source_index.numel(), dtype=torch.float64, device=idx.device)
+        return source_index, target_index, weights
+
+    def to_dataset(self, name: str) -> dict:
+        g = self.ugrid_topology
+        return {
+            f"{name}_node_x": g.node_x,
+            f"{name}_node_y": g.node_y,
+            f"{name}_face_node_connectivity": g.face_node_connectivity.astype(np.int64),
+            f"{name}_type": "UnstructuredGrid2d",
+        }
+
+
+class _StructuredAdapter:
+    """StructuredGrid2d promoted to quads (structured.py:489-501)."""
+
+    def __init__(self, grid: StructuredGrid2d):
+        self.grid = grid
+        self._promoted: Optional[UnstructuredGrid2d] = None
+
+    ndim = 2
+
+    @property
+    def dims(self):
+        return self.grid.dims
+
+    @property
+    def shape(self):
+        return self.grid.shape
+
+    @property
+    def size(self):
+        return self.grid.size
+
+    def to_unstructured(self) -> UnstructuredGrid2d:
+        if self._promoted is None:
+            self._promoted = UnstructuredGrid2d(self.grid.to_ugrid2d())
+        return self._promoted
+
+    def to_dataset(self, name: str) -> dict:
+        g = self.grid
+        return {
+            f"{name}_x": g.xbounds.index,
+            f"{name}_y": g.ybounds.index,
+            f"{name}_xbounds": g.xbounds.bounds,
+            f"{name}_ybounds": g.ybounds.bounds,
+            f"{name}_type": "StructuredGrid2d",
+        }
+
+
+def setup_grid(obj):
+    # regridder.py:72-80
+    if isinstance(obj, (Ugrid2d, UgridDataArray)):
+        return UnstructuredGrid2d(obj)
+    elif isinstance(obj, StructuredGrid2d):
+        return _StructuredAdapter(obj)
+    elif isinstance(obj, (UnstructuredGrid2d, _StructuredAdapter)):
+        return obj
+    else:
+        raise TypeError(
+            f"Expected Ugrid2d, UgridDataArray or StructuredGrid2d, received: {type(obj).__name__}"
+        )
+
+
+def _grid_from_dataset(ds: dict, prefix: str):
+    kind = ds[f"{prefix}_type"]
+    if kind == "UnstructuredGrid2d":
+        return Ugrid2d(ds[f"{prefix}_node_x"], ds[f"{prefix}_node_y"], -1,
+                       ds[f"{prefix}_face_node_connectivity"])
+    return StructuredGrid2d(ds[f"{prefix}_x"], ds[f"{prefix}_y"],
+                            xbounds=ds[f"{prefix}_xbounds"], ybounds=ds[f"{prefix}_ybounds"])
+
+
+class BaseRegridder(abc.ABC):
+    _METHODS: Tuple[str, ...] = ()
+
+    def __init__(self, source, target, tolerance: Optional[float] = None,
+                 target_range: Optional[Tuple[int, int]] = None):
+        self._source = setup_grid(source)
+        self._target = setup_grid(target)
+        self._weights = None
+        self._target_range = target_range
+        self._compute_weights(self._source, self._target, tolerance)
+
+    # ---- method selection (regridder.py:124-141) --------------------------------------
+    def _setup_regrid(self, func) -> None:
+        if isinstance(func, str):
+            if func not in self._METHODS:
+                raise ValueError(
+                    "Invalid regridding method. Available methods are: {}".format(self._METHODS)
+                )
+            self._method = sparse.METHOD_CODES[func]
+        elif isinstance(func, PercentileMethod):
+            self._method = (7, func.percentile)
+        elif callable(func):
+            raise NotImplementedError(
+                "custom Python reductions cannot run on the GPU; use a named method or "
+                "create_percentile_method(p)"
+            )
+        else:
+            raise TypeError(f"method must be string or callable, received: {type(func).__name__}")
+
+    @abc.abstractmethod
+    def _compute_weights(self, source, target, tolerance=None):
+        pass
+
+    def _regrid(self, source: torch.Tensor, A, size: int) -> torch.Tensor:
+        code, p = self._method
+        return sparse.csr_apply(code, p, source, A, size)
+
+    # ---- apply (regridder.py:143-262) ---------------------------------------------------
+    def _rows(self) -> int:
+        if self._target_range is None:
+            return self._target.size
+        return self._target_range[1] - self._target_range[0]
+
+    def regrid_device(self, source: torch.Tensor) -> torch.Tensor:
+        """(n_extra, source.size) float64 device tensor -> (n_extra, rows)."""
+        return self._regrid(source, self._weights, self._rows())
+
+    def _regrid_array(self, source):
+        source_grid = self._source
+        nd = source_grid.ndim
+        if source.ndim < nd or tuple(source.shape[source.ndim - nd:]) != tuple(source_grid.shape):
+            raise ValueError(
+                f"data does not contain regridder source dimensions: expected trailing shape "
+                f"{tuple(source_grid.shape)}, received {tuple(source.shape)}"
+            )
+        first_dims_shape = tuple(source.shape[: source.ndim - nd])
+        is_tensor = isinstance(source, torch.Tensor)
+        dev = self._weights.data.device
+        if is_tensor:
+            src = source.reshape((-1, source_grid.size)).to(dev, torch.float64).contiguous()
+        else:
+            a = np.ascontiguousarray(np.asarray(source).reshape((-1, source_grid.size)))
+            src = torch.from_numpy(a).to(dev, non_blocking=True).to(torch.float64)
+        out = self.regrid_device(src)
+        if self._target_range is None:
+            out_shape = first_dims_shape + tuple(self._target.shape)
+        else:
+            out_shape = first_dims_shape + (self._rows(),)
+        out = out.reshape(out_shape)
+        return out if is_tensor else out.cpu().numpy()
+
+    def regrid(self, data):
+        """regridder.py:212-262."""
+        if isinstance(data, UgridDataArray):
+            out = self._regrid_array(data.data)
+            if isinstance(self._target, UnstructuredGrid2d) and self._target_range is None:
+                return UgridDataArray(out, self._target.ugrid_topology,
+                                      data.dims[:-1] + (self._target.ugrid_topology.face_dimension,))
+            return out
+        elif isinstance(data, (np.ndarray, torch.Tensor)):
+            return self._regrid_array(data)
+        raise TypeError(
+            f"Expected UgridDataArray, numpy.ndarray or torch.Tensor, received: {type(data).__name__}"
+        )
+
+    # ---- persistence (regridder.py:264-361) -----------------------------------------------
+    def to_dataset(self) -> dict:
+        w = self._weights
+        if w is None:
+            raise ValueError("Weights have not been computed yet.")
+        ds = {}
+        if isinstance(w, MatrixCSR):
+            data, indices, indptr = w.to_numpy()
+            ds.update({"__regrid_data": data, "__regrid_indices": indices, "__regrid_indptr": indptr})
+        else:
+            data, row, col = w.to_numpy()
+            ds.update({"__regrid_data": data, "__regrid_row": row, "__regrid_col": col})
+        ds.update({"__regrid_n": w.n, "__regrid_m": w.m, "__regrid_nnz": w.nnz})
+        ds.update(self._source.to_dataset("__source"))
+        ds.update(self._target.to_dataset("__target"))
+        return ds
+
+    @property
+    def weights(self) -> dict:
+        return self.to_dataset()
+
+    def weights_as_dataframe(self):
+        import pandas as pd
+
+        matrix = self._weights
+        if matrix is None:
+            raise ValueError("Weights have not been computed yet.")
+        if isinstance(matrix, MatrixCSR):
+            matrix = matrix.to_coo()
+        data, row, col = matrix.to_numpy()
+        return pd.DataFrame({"target_index": row, "source_index": col, "weight": data})
+
+    @staticmethod
+    def _csr_from_dataset(ds: dict) -> MatrixCSR:
+        return MatrixCSR.from_arrays(ds["__regrid_data"], ds["__regrid_indices"], ds["__regrid_indptr"],
+                                     int(ds["__regrid_n"]), int(ds["__regrid_m"]))
+
+    @staticmethod
+    def _coo_from_dataset(ds: dict) -> MatrixCOO:
+        return MatrixCOO.from_triplet(ds["__regrid_row"], ds["__regrid_col"], ds["__regrid_data"],
+                                      n=int(ds["__regrid_n"]), m=int(ds["__regrid_m"]))
+
+    @classmethod
+    def _weights_from_dataset(cls, ds: dict):
+        return cls._csr_from_dataset(ds)
+
+    @classmethod
+    def from_weights(cls, weights: dict, target):
+        instance = cls.__new__(cls)
+        instance._weights = cls._weights_from_dataset(weights)
+        instance._target = setup_grid(target)
+        instance._source = setup_grid(_grid_from_dataset(weights, "__source"))
+        instance._target_range = None
+        return instance
+
+    @classmethod
+    def from_dataset(cls, dataset: dict):
+        target = _grid_from_dataset(dataset, "__target")
+        return cls.from_weights(dataset, target)
+
+
+class CentroidLocatorRegridder(BaseRegridder):
+    """regridder.py:364-426"""
+
+    def _compute_weights(self, source, target, tolerance=None):
+        src, tgt = source.to_unstructured(), target.to_unstructured()
+        if self._target_range is not None:
+            raise NotImplementedError("target_range is only supported by the overlap regridders")
+        source_index, target_index, weight_values = src.locate_centroids(tgt, tolerance)
+        self._weights = MatrixCOO(weight_values, target_index.contiguous(), source_index.contiguous(),
+                                  target.size, source.size, int(weight_values.numel()))
+
+    def _regrid(self, source, A, size):
+        return sparse.coo_gather(source, A, size)
+
+    @classmethod
+    def _weights_from_dataset(cls, ds: dict):
+        return cls._coo_from_dataset(ds)
+
+
+class BaseOverlapRegridder(BaseRegridder, abc.ABC):
+    def _overlap_weights(self, source, target, relative: bool) -> None:
+        # regridder.py:428-436
+        src, tgt = source.to_unstructured(), target.to_unstructured()
+        self._weights = src.overlap(tgt, relative=relative, target_range=self._target_range)
+
+
+class OverlapRegridder(BaseOverlapRegridder):
+    """regridder.py:454-532"""
+
+    _METHODS = ABSOLUTE_OVERLAP_METHODS
+
+    def __init__(self, source, target, method: Union[str, Callable] = "mean",
+                 target_range: Optional[Tuple[int, int]] = None):
+        super().__init__(source=source, target=target, target_range=target_range)
+        self._setup_regrid(method)
+
+    def _compute_weights(self, source, target, tolerance=None) -> None:
+        self._overlap_weights(source, target, relative=False)
+
+    @staticmethod
+    def create_percentile_method(percentile: float) -> PercentileMethod:
+        return create_percentile_method(percentile)
+
+    @classmethod
+    def from_weights(cls, weights: dict, target, method: Union[str, Callable] = "mean"):
+        instance = super().from_weights(weights, target)
+        instance._setup_regrid(method)
+        return instance
+
+
+class RelativeOverlapRegridder(BaseOverlapRegridder):
+    """regridder.py:535-586"""
+
+    _METHODS = RELATIVE_OVERLAP_METHODS
+
+    def __init__(self, source, target, method: Union[str, Callable] = "first_order_conservative",
+                 target_range: Optional[Tuple[int, int]] = None):
+        super().__init__(source=source, target=target, tolerance=None, target_range=target_range)
+        self._setup_regrid(method)
+
+    def _compute_weights(self, source, target, tolerance=None) -> None:
+        self._overlap_weights(source, target, relative=True)
+
+    @classmethod
+    def from_weights(cls, weights: dict, target,
+                     method: Union[str, Callable] = "first_order_conservative"):
+        instance = super().from_weights(weights, target)
+        instance._setup_regrid(method)
+        return instance
