@@ -109,6 +109,18 @@ int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32_t *d_indic
  * stats[3]=pairs that reached the clipper (C_clip) stats[4]=nnz
  * stats[5]=bbox candidates.  Valid after xg_overlap_begin. */
 int xg_overlap_stats(const xg_overlap *job, int64_t stats[8]);
+/* device time of each phase of xg_overlap_begin in milliseconds (CUDA events on
+ * the job's stream), indexed by xg_phase.  Valid after xg_overlap_begin. */
+typedef enum xg_phase {
+    XG_PHASE_PACK = 0,    /* Morton order + packing of the target faces */
+    XG_PHASE_COUNT = 1,   /* BVH walk, candidate count per target */
+    XG_PHASE_SCAN = 2,    /* candidate row pointer (+ size read-back) */
+    XG_PHASE_FILL = 3,    /* BVH walk, candidate write */
+    XG_PHASE_CLIP = 4,    /* separating-axis filter + Sutherland-Hodgman area */
+    XG_PHASE_ROWPTR = 5   /* positives per row + CSR row pointer */
+} xg_phase;
+#define XG_N_PHASES 6
+int xg_overlap_timings(const xg_overlap *job, double ms[8]);
 int xg_overlap_abort(xg_overlap *job);
 
 /* ---- point queries -------------------------------------------------------

@@ -1,0 +1,113 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol, the
+product refuses to run without a GPU, and the host-side logic behaves like the
+reference's."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import xugrid_b200 as xb
+from xugrid_b200 import _native, build, grid, regridder, synthetic
+from xugrid_b200.distributed import max_shard, shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build()
+    assert os.path.exists(path)
+    header = open(os.path.join(ROOT, "include", "xg_regrid.h")).read()
+    declared = set(re.findall(r"\b(xg_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    lib = _native.load_library()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.xg_abi_version() == 1
+
+
+def test_sass_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", build.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    xy, faces = synthetic.disk()
+    with pytest.raises(_native.XgError):
+        xb.CellTree2d(xy, faces)
+    g = xb.Ugrid2d(xy[:, 0], xy[:, 1], -1, faces)
+    with pytest.raises(_native.XgError):
+        xb.OverlapRegridder(g, g)
+
+
+def test_ugrid2d_normalises_connectivity():
+    # ugrid2d.py:103-109
+    xy, faces = synthetic.jittered_lattice(3, 2, 0, "mixed")
+    f1 = faces.copy()
+    f1[f1 >= 0] += 1
+    f1[f1 < 0] = -999
+    g = xb.Ugrid2d(xy[:, 0], xy[:, 1], -999, f1, start_index=1)
+    assert np.array_equal(g.face_node_connectivity, faces)
+    assert g.n_face == len(faces) and g.n_node == len(xy)
+    with pytest.raises(TypeError):
+        xb.Ugrid2d(xy[:, 0], xy[:, 1], -1, [[0, 1, 2]])
+
+
+def test_from_structured_bounds_is_ccw_quads():
+    # ugrid2d.py:1894-1912,1973-2034
+    xb_ = np.array([[0.0, 1.0], [1.0, 2.5], [2.5, 3.0]])
+    yb_ = np.array([[8.0, 10.0], [7.0, 8.0]])  # rows descending, each row [lower, upper]
+    g = xb.Ugrid2d.from_structured_bounds(xb_, yb_)
+    assert g.n_face == 6 and g.face_node_connectivity.shape == (6, 4)
+    xyc = g.node_coordinates[g.face_node_connectivity]
+    d1 = xyc[:, 1] - xyc[:, 0]
+    d2 = xyc[:, 2] - xyc[:, 1]
+    assert ((d1[:, 0] * d2[:, 1] - d1[:, 1] * d2[:, 0]) > 0).all()
+    with pytest.raises(ValueError):
+        grid.bounds1d_to_vertices(np.array([[0.0, 1.0], [3.0, 2.0], [1.0, 1.5]]))
+
+
+def test_structured_grid_bounds_inference():
+    # structured.py:24-100
+    s = xb.StructuredGrid2d(x=np.array([0.5, 1.5, 2.5]), y=np.array([3.5, 2.5]))
+    assert s.shape == (2, 3) and s.size == 6 and s.dims == ("y", "x")
+    assert np.allclose(s.xbounds.bounds, [[0, 1], [1, 2], [2, 3]])
+    assert s.ybounds.flipped and np.allclose(s.ybounds.directional_bounds, [[3, 4], [2, 3]])
+    with pytest.raises(ValueError):
+        xb.StructuredGrid2d(x=np.array([0.0, 1.0, 3.0]), y=np.array([0.0, 1.0]))
+    with pytest.raises(ValueError):
+        xb.StructuredGrid2d(x=np.array([0.0, 2.0, 1.0]), y=np.array([0.0, 1.0]))
+
+
+def test_percentile_method_validation():
+    # reduce.py:241-248, tests/test_regrid/test_regridder.py:282-293
+    m = xb.OverlapRegridder.create_percentile_method(33.3)
+    assert m.percentile == 33.3
+    with pytest.raises(ValueError):
+        xb.create_percentile_method(-1.0)
+    with pytest.raises(ValueError):
+        xb.create_percentile_method(100.5)
+
+
+def test_setup_grid_type_errors():
+    # regridder.py:72-80, unstructured.py:77-81
+    with pytest.raises(TypeError):
+        regridder.setup_grid(np.zeros(3))
+    with pytest.raises(TypeError):
+        regridder.UnstructuredGrid2d("nope")
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 10, 1000003):
+        for world in (1, 2, 3, 8):
+            ranges = [shard_range(n, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            for (a, b), (c, d) in zip(ranges[:-1], ranges[1:]):
+                assert b == c
+            assert max(b - a for a, b in ranges) == max_shard(n, world) or n == 0
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)

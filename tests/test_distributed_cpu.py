@@ -1,0 +1,60 @@
+"""world_size-2 gloo test of the sharded output assembly (runs on CPU)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from xugrid_b200 import synthetic
+from xugrid_b200.distributed import all_gather_columns, shard_range
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_total, n_extra, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank regrids only its own target range (the oracle stands in
+        # for the GPU here: this test is about the host-side sharding logic)
+        sxy, sf = synthetic.delaunay(400, 1)
+        txy, tf = synthetic.jittered_lattice(9, 7, 2, "tri", bounds=(0.1, 0.9, 0.1, 0.9))
+        assert len(tf) == n_total
+        b, e = shard_range(n_total, rank, world)
+        tree = oracle.CellTree2d(sxy, sf)
+        ti, si, w = tree.intersect_faces(txy, tf[b:e])
+        indptr = oracle.coo_to_csr(ti, e - b)
+        vals = np.random.default_rng(3).random((n_extra, len(sf)))
+        local = torch.from_numpy(oracle.csr_apply("mean", vals, w, si, indptr, e - b))
+        full = all_gather_columns(local, n_total)
+        if rank == 0:
+            ti, si, w = tree.intersect_faces(txy, tf)
+            indptr = oracle.coo_to_csr(ti, n_total)
+            ref = oracle.csr_apply("mean", vals, w, si, indptr, n_total)
+            q.put(bool(np.array_equal(full.numpy(), ref, equal_nan=True)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_regrid_matches_single():
+    world, n_total, n_extra = 2, 126, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, n_extra, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True

@@ -1,0 +1,204 @@
+"""GPU tests of the regridder classes, modelled on the reference's
+tests/test_regrid/test_regridder.py and test_unstructured.py, plus end-to-end
+parity of BASELINE config 1 (5k-face Delaunay -> 50x50 raster) against the
+oracle pipeline."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests import cases
+from xugrid_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def xb():
+    import xugrid_b200
+
+    assert torch.cuda.is_available()
+    return xugrid_b200
+
+
+@pytest.fixture(scope="module")
+def disk(xb):
+    xy, faces = synthetic.disk()
+    grid = xb.Ugrid2d(xy[:, 0], xy[:, 1], -1, faces)
+    cent = oracle.face_centroids(xy, faces)
+    z = synthetic.function_z(cent[:, 0], cent[:, 1])
+    return xb.UgridDataArray(z, grid)
+
+
+def quads(xb, dx):
+    # tests/fixtures/fixture_regridder.py:39-90
+    xmin, ymin, xmax, ymax = -10.0, -10.0, 10.0, 10.0
+    x = np.arange(xmin, xmax, dx) + 0.5 * dx
+    y = np.arange(ymin, ymax, dx) + 0.5 * dx
+    return xb.StructuredGrid2d(x, y)
+
+
+def test_check_source_target_types(xb, disk):
+    for cls in (xb.CentroidLocatorRegridder, xb.OverlapRegridder, xb.RelativeOverlapRegridder):
+        with pytest.raises(TypeError):
+            cls(source=disk, target=1.0)
+        with pytest.raises(TypeError):
+            cls(source=1.0, target=disk)
+
+
+def test_overlap_regridder(xb, disk):
+    # test_regridder.py:152-167
+    square = quads(xb, 2.0).to_ugrid2d()
+    assert square.n_face == 100
+    regridder = xb.OverlapRegridder(disk, square, method="mean")
+    result = regridder.regrid(disk)
+    assert isinstance(result, xb.UgridDataArray)
+    v = result.values
+    assert np.isfinite(v).any()
+    assert np.nanmin(v) >= disk.values.min() and np.nanmax(v) <= disk.values.max()
+    layered = xb.UgridDataArray(np.ones(5)[:, None] * disk.values[None, :], disk.grid, ("layer", disk.grid.face_dimension))
+    broadcasted = regridder.regrid(layered)
+    assert broadcasted.dims == ("layer", square.face_dimension)
+    assert broadcasted.shape == (5, 100)
+    assert np.array_equal(broadcasted.values[3], v, equal_nan=True)
+
+
+def test_centroid_locator_regridder(xb, disk):
+    # test_regridder.py:100-127
+    square = quads(xb, 2.0).to_ugrid2d()
+    regridder = xb.CentroidLocatorRegridder(source=disk, target=square)
+    result = regridder.regrid(disk)
+    v = result.values
+    assert np.isfinite(v).any()
+    assert np.nanmin(v) >= disk.values.min() and np.nanmax(v) <= disk.values.max()
+    # parity with the oracle's locate
+    cent = oracle.face_centroids(square.node_coordinates, square.face_node_connectivity)
+    idx = oracle.CellTree2d(disk.grid.node_coordinates, disk.grid.face_node_connectivity).locate_points(cent)
+    expect = np.where(idx >= 0, disk.values[idx.clip(0)], np.nan)
+    assert np.array_equal(v, expect, equal_nan=True)
+    back = xb.CentroidLocatorRegridder(source=result, target=disk).regrid(result)
+    assert back.grid.n_face == disk.grid.n_face
+
+
+@pytest.mark.parametrize("method", ["mean", "sum", "minimum", "maximum", "mode", "median", "max_overlap",
+                                    "harmonic_mean", "geometric_mean", "p25"])
+def test_config1_delaunay_to_raster_matches_oracle(xb, method):
+    """BASELINE.json configs[0]: 5k-face Delaunay -> 50x50 structured target."""
+    sxy = np.random.default_rng(1).random((2600, 2))
+    from scipy.spatial import Delaunay
+
+    sf = Delaunay(sxy).simplices.astype(np.int64)
+    source = xb.Ugrid2d(sxy[:, 0], sxy[:, 1], -1, sf)
+    cx = np.linspace(0.01, 0.99, 50)
+    target = xb.StructuredGrid2d(cx, cx)
+    values = np.random.default_rng(2).random(len(sf))
+    values[::17] = np.nan
+    out = xb.OverlapRegridder(source, target, method=method).regrid(values)
+    assert out.shape == (50, 50)
+    # oracle pipeline: promote raster, intersect, to_csr, reduce
+    tgrid = target.to_ugrid2d()
+    si, ti, w = oracle.overlap_triplets(sxy, sf, tgrid.node_coordinates, tgrid.face_node_connectivity)
+    o = cases.canon(ti, si, w)
+    indptr = oracle.coo_to_csr(o[0], 2500)
+    ref = oracle.csr_apply(method, values, o[2], o[1], indptr, 2500).reshape(50, 50)
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    if method == "geometric_mean":
+        assert np.allclose(out, ref, rtol=1e-10, atol=0, equal_nan=True)
+    else:
+        assert np.array_equal(out, ref, equal_nan=True)
+
+
+def test_relative_overlap_conservative(xb):
+    sxy, sf = synthetic.jittered_lattice(30, 30, 1, "mixed")
+    txy, tf = synthetic.jittered_lattice(11, 12, 2, "tri", bounds=(0.1, 0.9, 0.1, 0.9))
+    source = xb.Ugrid2d(sxy[:, 0], sxy[:, 1], -1, sf)
+    target = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf)
+    values = np.random.default_rng(3).random((4, len(sf)))
+    r = xb.RelativeOverlapRegridder(source, target)
+    out = r.regrid(values)
+    si, ti, w = oracle.overlap_triplets(sxy, sf, txy, tf, relative=True)
+    o = cases.canon(ti, si, w)
+    ref = oracle.csr_apply("first_order_conservative", values, o[2], o[1], oracle.coo_to_csr(o[0], len(tf)), len(tf))
+    assert np.array_equal(out, ref, equal_nan=True)
+    with pytest.raises(ValueError):
+        xb.RelativeOverlapRegridder(source, target, method="mean")
+
+
+def test_method_errors(xb, disk):
+    # regridder.py:124-141
+    square = quads(xb, 4.0)
+    with pytest.raises(ValueError, match="Invalid regridding method"):
+        xb.OverlapRegridder(disk, square, method="nope")
+    with pytest.raises(TypeError):
+        xb.OverlapRegridder(disk, square, method=3.5)
+    with pytest.raises(NotImplementedError):
+        xb.OverlapRegridder(disk, square, method=lambda v, w, ws: 0.0)
+    r = xb.OverlapRegridder(disk, square, method=xb.OverlapRegridder.create_percentile_method(50))
+    m = xb.OverlapRegridder(disk, square, method="median")
+    assert np.array_equal(r.regrid(disk), m.regrid(disk), equal_nan=True)
+    with pytest.raises(TypeError):
+        r.regrid([1, 2, 3])
+    with pytest.raises(ValueError):
+        r.regrid(np.zeros(7))
+    median = xb.OverlapRegridder.create_percentile_method(percentile=50)
+    assert median(np.array([0, 1, 2, 3, 4], dtype=float), np.ones(5), np.zeros(5)) == 2
+
+
+@pytest.mark.parametrize("cls_name", ["CentroidLocatorRegridder", "OverlapRegridder", "RelativeOverlapRegridder"])
+def test_regridder_from_weights_and_dataset(xb, disk, cls_name):
+    # test_regridder.py:203-257
+    cls = getattr(xb, cls_name)
+    square = quads(xb, 2.0).to_ugrid2d()
+    regridder = cls(source=disk, target=square)
+    result = regridder.regrid(disk)
+    weights = regridder.weights
+    assert weights["__regrid_n"] == 100 and weights["__source_type"] == "UnstructuredGrid2d"
+    new = cls.from_weights(weights, target=square)
+    assert np.array_equal(new.regrid(disk).values, result.values, equal_nan=True)
+    layered = np.stack([disk.values * k for k in (1.0, 2.0, 3.0)])
+    assert np.array_equal(new.regrid(layered)[0], result.values, equal_nan=True)
+    again = cls.from_dataset(regridder.to_dataset())
+    assert np.array_equal(again.regrid(disk).values, result.values, equal_nan=True)
+    df = regridder.weights_as_dataframe()
+    assert {"source_index", "target_index", "weight"} <= set(df.columns)
+    regridder._weights = None
+    with pytest.raises(ValueError):
+        regridder.weights_as_dataframe()
+
+
+def test_structured_source_to_unstructured_target(xb, disk):
+    # test_regridder.py:41-55
+    src = quads(xb, 1.0)
+    data = np.ones(src.shape)
+    for cls in (xb.CentroidLocatorRegridder, xb.OverlapRegridder, xb.RelativeOverlapRegridder):
+        out = cls(src, disk).regrid(data)
+        assert out.shape == (disk.grid.n_face,)
+        assert np.nanmax(out) <= 1.0 + 1e-12
+
+
+def test_self_overlap_locate_identity(xb, disk):
+    # tests/test_regrid/test_unstructured.py:32-59
+    g = disk.grid
+    tree = g.celltree
+    ti, si, w = tree.intersect_faces(g.node_coordinates, g.face_node_connectivity)
+    valid = w > 1e-5
+    assert np.array_equal(ti[valid], np.arange(g.n_face)) and np.array_equal(si[valid], np.arange(g.n_face))
+    assert np.allclose(w[valid], g.area)
+    assert np.array_equal(g.locate_points(g.centroids), np.arange(g.n_face))
+
+
+def test_torch_tensor_in_tensor_out_and_target_range(xb):
+    sxy, sf = synthetic.delaunay(1500, 3)
+    txy, tf = synthetic.delaunay(1200, 4)
+    source = xb.Ugrid2d(sxy[:, 0], sxy[:, 1], -1, sf)
+    target = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf)
+    v = torch.rand(3, len(sf), dtype=torch.float64, device="cuda")
+    full = xb.OverlapRegridder(source, target).regrid(v)
+    assert isinstance(full, torch.Tensor) and full.is_cuda and full.shape == (3, len(tf))
+    parts = []
+    from xugrid_b200.distributed import shard_range
+
+    for r in range(3):
+        b, e = shard_range(len(tf), r, 3)
+        parts.append(xb.OverlapRegridder(source, target, target_range=(b, e)).regrid(v))
+    assert torch.equal(torch.cat(parts, dim=1).nan_to_num(-1.0), full.nan_to_num(-1.0))

@@ -1,0 +1,144 @@
+"""CPU tests: the oracle against the reference's golden vectors and known
+answers.  No GPU needed."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import cases
+from xugrid_b200 import synthetic
+
+
+def test_apply_golden(golden_dir):
+    g = np.load(f"{golden_dir}/apply_golden.npz")
+    n = int(g["n"])
+    checked = 0
+    for key in g.files:
+        if not key.startswith("out_"):
+            continue
+        name = key[4:]
+        if name.startswith("percentile_"):
+            out = oracle.csr_apply("percentile", g["source"], g["data"], g["indices"], g["indptr"], n,
+                                   percentile=float(name.split("_")[1]))
+        elif name == "int_mean":
+            out = oracle.csr_apply("mean", g["int_source"], g["data"], g["indices"], g["indptr"], n)
+        else:
+            out = oracle.csr_apply(name, g["source"], g["data"], g["indices"], g["indptr"], n)
+        # the C restatement is bit-identical to the reference's numba code
+        assert np.array_equal(out, g[key], equal_nan=True), name
+        checked += 1
+    assert checked == 22
+    # the parallel-rows schedule gives the same numbers
+    out = oracle.csr_apply("mean", g["source"], g["data"], g["indices"], g["indptr"], n, parallel_rows=True)
+    assert np.array_equal(out, g["out_mean"], equal_nan=True)
+
+
+def test_coo_golden(golden_dir):
+    c = np.load(f"{golden_dir}/coo_golden.npz")
+    out = oracle.coo_gather(c["source"], c["row"], c["col"], int(c["size"]))
+    assert np.array_equal(out, c["out"], equal_nan=True)
+    assert np.array_equal(oracle.coo_to_csr(c["row"], int(c["size"])), c["indptr"])
+
+
+def test_connectivity_golden(golden_dir):
+    k = np.load(f"{golden_dir}/connectivity_golden.npz")
+    assert np.array_equal(oracle.face_area(k["xy"], k["faces"]), k["area"])
+    assert np.array_equal(oracle.face_centroids(k["xy"], k["faces"]), k["centroids"])
+    assert np.array_equal(oracle.face_area(k["xy"], k["tri"]), k["tri_area"])
+    assert np.array_equal(oracle.face_centroids(k["xy"], k["tri"]), k["tri_centroids"])
+    assert np.array_equal(oracle.counter_clockwise(k["xy"], k["cw"]), k["ccw"])
+
+
+@pytest.mark.parametrize("case", cases.reduce_cases_as_csr(), ids=lambda c: f"{c[0]}-{c[1]}")
+def test_reduce_known_answers(case):
+    method, p, src, data, indices, indptr, expected = case
+    out = oracle.csr_apply(method, src, data, indices, indptr, len(expected), percentile=p)[0]
+    assert np.allclose(out, expected, equal_nan=True)
+
+
+def test_locate_points_known_answers():
+    # tests/test_ugrid2d.py:724-730
+    t = oracle.CellTree2d(cases.VERTICES, cases.FACES, -1)
+    assert np.array_equal(t.locate_points(cases.CENTROIDS), [0, 1, 2, 3])
+    assert np.array_equal(t.locate_points([[-0.01, 1.0], [-0.01, 0.5]], 0.011), [0, 0])
+
+
+def test_barycentric_known_answers():
+    # tests/test_ugrid2d.py:751-791
+    t = oracle.CellTree2d(cases.VERTICES, cases.FACES, -1)
+    face, w = t.compute_barycentric_weights(cases.BARY_XY)
+    assert np.array_equal(face, cases.BARY_FACE)
+    assert np.allclose(w, cases.BARY_W)
+    xy = cases.BARY_XY.copy()
+    xy[:, 0] -= 0.01
+    face, w = t.compute_barycentric_weights(xy, tolerance=0.01)
+    assert np.array_equal(face, cases.BARY_FACE_TOL)
+    assert np.allclose(w, cases.BARY_W_TOL, atol=0.05)
+
+
+def test_rasterize_known_answers():
+    # tests/test_ugrid2d.py:794-825
+    t = oracle.CellTree2d(cases.VERTICES, cases.FACES, -1)
+    x = np.array([0.25, 0.75, 1.25, 1.75]); y = np.array([1.75, 1.25, 0.75, 0.25])
+    yy, xx = np.meshgrid(y, x, indexing="ij")
+    idx = t.locate_points(np.column_stack([xx.ravel(), yy.ravel()])).reshape(4, 4)
+    assert np.array_equal(idx, cases.RASTER_INDEX)
+    x = np.array([-0.75, -0.25, 0.25, 0.75, 1.25, 1.75]); y = np.array([1.75, 1.25, 0.75, 0.25, -0.25, -0.75])
+    yy, xx = np.meshgrid(y, x, indexing="ij")
+    idx = t.locate_points(np.column_stack([xx.ravel(), yy.ravel()])).reshape(6, 6)
+    assert np.array_equal(idx, cases.RASTER_INDEX_BOUNDS)
+
+
+def test_self_overlap_is_identity():
+    # tests/test_regrid/test_unstructured.py:32-45
+    xy, faces = synthetic.disk()
+    tree = oracle.CellTree2d(xy, faces)
+    ti, si, w = tree.intersect_faces(xy, faces)
+    valid = w > 1e-5
+    assert np.array_equal(ti[valid], np.arange(len(faces)))
+    assert np.array_equal(si[valid], np.arange(len(faces)))
+    assert np.allclose(w[valid], oracle.face_area(xy, faces))
+    # self-locate / self-barycentric identity (test_unstructured.py:47-59)
+    cent = oracle.face_centroids(xy, faces)
+    assert np.array_equal(tree.locate_points(cent), np.arange(len(faces)))
+
+
+def test_tree_equals_bruteforce_and_invariants():
+    sxy, sf = synthetic.delaunay(1500, 3)
+    txy, tf = synthetic.jittered_lattice(23, 19, 4, "mixed", bounds=(0.1, 0.9, 0.1, 0.9))
+    tree = oracle.CellTree2d(sxy, sf)
+    a = cases.canon(*tree.intersect_faces(txy, tf))
+    b = cases.canon(*tree.intersect_faces_bruteforce(txy, tf))
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    # targets lie strictly inside the source hull: row sums equal target areas
+    ta = oracle.face_area(txy, tf)
+    rs = np.bincount(a[0], weights=a[2], minlength=len(ta))
+    assert np.allclose(rs, ta, rtol=1e-9)
+    # symmetry: overlap(A, B)^T == overlap(B, A)
+    tree2 = oracle.CellTree2d(txy, tf)
+    ti2, si2, w2 = tree2.intersect_faces(sxy, sf)
+    c = cases.canon(si2, ti2, w2)
+    assert np.array_equal(c[0], a[0]) and np.array_equal(c[1], a[1])
+    assert np.allclose(c[2], a[2], rtol=1e-9, atol=1e-18)
+
+
+def test_orientation_independence():
+    # tests/test_regrid/test_regridder.py:295-332: flipping faces changes nothing
+    sxy, sf = synthetic.jittered_lattice(9, 8, 1, "mixed")
+    txy, tf = synthetic.jittered_lattice(7, 11, 2, "tri")
+    cw = sf.copy()
+    for r in range(len(cw)):
+        n = 4 if cw[r, 3] != -1 else 3
+        cw[r, :n] = cw[r, :n][::-1]
+    a = cases.canon(*oracle.CellTree2d(sxy, sf).intersect_faces(txy, tf))
+    b = cases.canon(*oracle.CellTree2d(sxy, cw).intersect_faces(txy, tf))
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.allclose(a[2], b[2], rtol=1e-12)
+
+
+def test_empty_inputs():
+    xy, faces = synthetic.disk()
+    tree = oracle.CellTree2d(xy, faces)
+    ti, si, w = tree.intersect_faces(xy + 100.0, faces)
+    assert ti.size == 0 and si.size == 0 and w.size == 0
+    assert np.array_equal(tree.locate_points(np.array([[50.0, 50.0]])), [-1])

@@ -36,6 +36,7 @@ SIGNATURES = {
     ),
     "xg_overlap_finish": (_int, [_vp, _vp, _vp, _vp, _int, _vp]),
     "xg_overlap_stats": (_int, [_vp, ctypes.POINTER(_i64)]),
+    "xg_overlap_timings": (_int, [_vp, ctypes.POINTER(_dbl)]),
     "xg_overlap_abort": (_int, [_vp]),
     "xg_locate_points": (_int, [_vp, _vp, _i64, _dbl, _vp, _vp]),
     "xg_barycentric": (_int, [_vp, _vp, _i64, _dbl, _vp, _vp, _vp]),

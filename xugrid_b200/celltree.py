@@ -69,6 +69,9 @@ def faces_to_device(faces: ArrayLike, fill_value: int, device: torch.device) -> 
     return t
 
 
+PHASES = ("pack", "count", "scan", "fill", "clip", "rowptr")
+
+
 class OverlapStats(NamedTuple):
     targets: int
     node_visits: int
@@ -105,6 +108,7 @@ class CellTree2d:
         self.device_bytes = int(info[3])
         self.default_tolerance = float(tol.value)
         self.last_stats: Optional[OverlapStats] = None
+        self.last_phase_ms: dict = {}
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -151,6 +155,9 @@ class CellTree2d:
             st = (ctypes.c_int64 * 8)()
             _native.check(L.xg_overlap_stats(job, st))
             self.last_stats = OverlapStats(*[int(st[i]) for i in range(6)])
+            ms = (ctypes.c_double * 8)()
+            _native.check(L.xg_overlap_timings(job, ms))
+            self.last_phase_ms = dict(zip(PHASES, [float(ms[i]) for i in range(len(PHASES))]))
             indices = torch.empty(nnz.value, dtype=torch.int32, device=self.device)
             area = torch.empty(nnz.value, dtype=torch.float64, device=self.device)
             _native.check(

@@ -266,6 +266,23 @@ struct xg_overlap {
     DevBuf tperm, tbox, tpoly, tnv, cand_ptr, cand_src, cand_tgt, area, stats;
     int64_t h_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool stats_valid = false;
+    // phase timing: ev[i] is recorded when phase i starts, ev[n_ev-1] at the end
+    cudaEvent_t ev[XG_N_PHASES + 1];
+    int n_ev = 0;
+    double h_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    xg_overlap() { for (int i = 0; i <= XG_N_PHASES; ++i) ev[i] = nullptr; }
+    ~xg_overlap() { for (int i = 0; i <= XG_N_PHASES; ++i) if (ev[i]) cudaEventDestroy(ev[i]); }
+    cudaError_t mark() {
+        cudaError_t e = cudaEventCreate(&ev[n_ev]);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(ev[n_ev++], s);
+    }
+    void collect() {
+        for (int i = 0; i + 1 < n_ev; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) h_ms[i] = ms;
+        }
+    }
 };
 
 extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, int64_t n_t_node,
@@ -298,6 +315,7 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
             *job_out = job;
             return XG_OK;
         }
+        OV_CUDA(job->mark());  // XG_PHASE_PACK
         OV_CUDA(job->tperm.alloc(sizeof(int32_t) * (size_t)n_t, s));
         OV_CUDA(job->tbox.alloc(sizeof(Box) * (size_t)n_t, s));
         OV_CUDA(job->tpoly.alloc(sizeof(double) * 2 * (size_t)k_t * (size_t)n_t, s));
@@ -316,12 +334,14 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
         const unsigned tblocks = (unsigned)div_up(tiles, TRAV_WARPS);
 
         // count pass
+        OV_CUDA(job->mark());  // XG_PHASE_COUNT
         DevBuf cnt;
         OV_CUDA(cnt.alloc(sizeof(int32_t) * (size_t)(n_t + 1), s));
         OV_CUDA(cudaMemsetAsync(cnt.as<int32_t>() + n_t, 0, sizeof(int32_t), s));
         k_traverse<false><<<tblocks, TRAV_WARPS * 32, 0, s>>>(P, job->tbox.as<Box>(), n_t, cnt.as<int32_t>(), nullptr,
                                                              nullptr, nullptr, job->stats.as<unsigned long long>());
         OV_CUDA(cudaGetLastError());
+        OV_CUDA(job->mark());  // XG_PHASE_SCAN
         OV_CUDA(job->cand_ptr.alloc(sizeof(int64_t) * (size_t)(n_t + 1), s));
         {
             cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(cnt.as<int32_t>(), CastI64());
@@ -337,6 +357,7 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
         job->n_cand = n_cand;
 
         // fill pass
+        OV_CUDA(job->mark());  // XG_PHASE_FILL
         OV_CUDA(job->cand_src.alloc(sizeof(int32_t) * (size_t)n_cand, s));
         OV_CUDA(job->cand_tgt.alloc(sizeof(int32_t) * (size_t)n_cand, s));
         OV_CUDA(job->area.alloc(sizeof(double) * (size_t)n_cand, s));
@@ -345,6 +366,7 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
         OV_CUDA(cudaGetLastError());
 
         // clip
+        OV_CUDA(job->mark());  // XG_PHASE_CLIP
         if (n_cand > 0) {
             const int ks = source->k;
             const int32_t *ct = job->cand_tgt.as<int32_t>(), *cs = job->cand_src.as<int32_t>();
@@ -362,6 +384,7 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
         }
 
         // CSR row pointer in the caller's row order (cnt is reused as row counts)
+        OV_CUDA(job->mark());  // XG_PHASE_ROWPTR
         k_row_count<<<(unsigned)div_up(n_t, 256), 256, 0, s>>>(job->cand_ptr.as<int64_t>(), job->area.as<double>(),
                                                               job->tperm.as<int32_t>(), t_begin, n_t, cnt.as<int32_t>());
         OV_CUDA(cudaGetLastError());
@@ -377,7 +400,9 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
         unsigned long long hs[8];
         OV_CUDA(cudaMemcpyAsync(&nnz, d_indptr + n_t, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         OV_CUDA(cudaMemcpyAsync(hs, job->stats.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+        OV_CUDA(job->mark());  // end
         OV_CUDA(cudaStreamSynchronize(s));
+        job->collect();
         job->nnz = nnz;
         job->h_stats[0] = n_t;
         job->h_stats[1] = (int64_t)hs[0] * 2;  // the walk runs twice (count + fill)
@@ -420,6 +445,12 @@ extern "C" int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32
 extern "C" int xg_overlap_stats(const xg_overlap *job, int64_t stats[8]) {
     if (!job || !stats || !job->stats_valid) { set_error("xg_overlap_stats: no stats"); return XG_ERR_INVALID; }
     for (int i = 0; i < 8; ++i) stats[i] = job->h_stats[i];
+    return XG_OK;
+}
+
+extern "C" int xg_overlap_timings(const xg_overlap *job, double ms[8]) {
+    if (!job || !ms || !job->stats_valid) { set_error("xg_overlap_timings: no timings"); return XG_ERR_INVALID; }
+    for (int i = 0; i < 8; ++i) ms[i] = job->h_ms[i];
     return XG_OK;
 }
 

@@ -1,0 +1,65 @@
+"""
+Multi-GPU sharding of the regridding path (one process per GPU).
+
+Every target face owns one CSR row and one output column, so the path shards
+with no exchange during the build or the apply: rank r builds and applies the
+contiguous target range ``shard_range(n_target, r, world)`` against a
+replicated source mesh.  The only collective is one all-gather that
+reassembles the (n_extra, n_target) output (NCCL over NVLink on the GPU box;
+gloo in the CPU tests).  The reference has no counterpart: its only
+parallelism is numba prange over the extra axis
+(/root/reference/xugrid/regrid/regridder.py:50).
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [begin, end) of n items for `rank` of `world`;
+    the first n % world ranks get one extra item."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("invalid rank/world")
+    base, rem = divmod(n, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def max_shard(n: int, world: int) -> int:
+    return (n + world - 1) // world
+
+
+def all_gather_columns(local: torch.Tensor, n_total: int, group: Optional[dist.ProcessGroup] = None,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """
+    ``local`` is this rank's (n_extra, rows_local) block of columns
+    ``shard_range(n_total, rank, world)``.  Returns the full (n_extra, n_total)
+    array on every rank with ONE all_gather_into_tensor of equally sized,
+    padded slabs laid out [rank][n_extra][max_shard].
+    """
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local if out is None else out.copy_(local)
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_extra = int(local.shape[0])
+    pad = max_shard(n_total, world)
+    b, e = shard_range(n_total, rank, world)
+    if local.shape[1] != e - b:
+        raise ValueError(f"rank {rank} holds {local.shape[1]} columns, expected {e - b}")
+    send = local.new_empty((n_extra, pad))
+    send[:, : e - b] = local
+    if e - b < pad:
+        send[:, e - b :] = 0
+    recv = local.new_empty((world * n_extra, pad))  # concatenation along dim 0
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, n_extra, pad)
+    if out is None:
+        out = local.new_empty((n_extra, n_total))
+    for r in range(world):
+        rb, re = shard_range(n_total, r, world)
+        out[:, rb:re] = recv[r, :, : re - rb]
+    return out

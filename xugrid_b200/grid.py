@@ -22,6 +22,7 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
+from . import _native
 from .celltree import CellTree2d, face_area_device, face_centroid_device, faces_to_device, to_device
 
 FILL_VALUE = -1
@@ -103,6 +104,7 @@ class Ugrid2d:
     def device_arrays(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """(n_node, 2) float64 and (n_face, k) int tensors in HBM (cached)."""
         if self._xy_d is None:
+            _native.lib()  # raises when there is no GPU: no CPU fallback
             dev = self._dev()
             self._xy_d = to_device(self.node_coordinates, torch.float64, dev)
             self._faces_d = faces_to_device(self.face_node_connectivity, FILL_VALUE, dev)

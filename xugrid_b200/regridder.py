@@ -40,8 +40,24 @@ class PercentileMethod:
             raise ValueError(f"percentile must be in the range [0, 100], received: {p}")
         self.percentile = float(p)
 
-    def __call__(self, values, weights, workspace=None):  # host evaluation for inspection only
-        raise NotImplementedError("percentile methods are evaluated on the GPU")
+    def __call__(self, values, weights, workspace=None):
+        """Host evaluation of reduce.percentile (reduce.py:161-203) for one row;
+        the regridders evaluate the same rule on the GPU."""
+        values = np.asarray(values, dtype=np.float64)
+        weights = np.asarray(weights, dtype=np.float64)
+        if weights.size == 0 or weights.max() == 0.0:
+            return np.nan
+        v = np.sort(values[~np.isnan(values)])
+        if v.size == 0:
+            return np.nan
+        if self.percentile == 0 or v.size == 1:
+            return v[0]
+        if self.percentile == 100:
+            return v[-1]
+        rank = 1 + (v.size - 1) * self.percentile / 100.0
+        f = int(np.floor(rank))
+        m = rank - f
+        return v[f - 1] * (1 - m) + v[f] * m
 
 
 def create_percentile_method(p: float) -> PercentileMethod:
