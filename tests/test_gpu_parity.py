@@ -352,7 +352,7 @@ def test_full_size_properties(xb):
     # (4) mean of a constant field is the constant; linearity of the conservative sum
     A = sparse.MatrixCSR(area, indices, indptr, n_t, n_s, int(area.numel()))
     ones = torch.full((1, n_s), 3.25, dtype=torch.float64, device="cuda")
-    assert bool((sparse.csr_apply(0, 0.0, ones, A, n_t) == 3.25).all())
+    assert torch.allclose(sparse.csr_apply(0, 0.0, ones, A, n_t), ones[:, :1].expand(1, n_t), rtol=1e-14, atol=0)
     v1 = torch.rand(1, n_s, dtype=torch.float64, device="cuda")
     v2 = torch.rand(1, n_s, dtype=torch.float64, device="cuda")
     c = lambda v: sparse.csr_apply(9, 0.0, v, A, n_t)

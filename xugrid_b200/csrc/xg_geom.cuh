@@ -150,6 +150,186 @@ __device__ __forceinline__ double clip_area(const double2 (&poly)[KT], int np,
     return 0.5 * area;
 }
 
+// ---------------------------------------------------------------------------
+// Warp-uniform variants used by the dense clipping kernel.  Same arithmetic,
+// same results as polygons_intersect() / clip_area() above, but written as
+// straight-line code over fixed trip counts with predicates, so the 32 lanes
+// of a warp never execute different instructions: ptxas otherwise unrolls the
+// data-dependent loops with per-length entry points and the lanes serialise
+// (measured: 17-53 % of lanes active, profiles/r1_v1*, r1_v2*).
+
+template <int KA, int KB>
+__device__ __forceinline__ bool axis_separates(double nx, double ny, const double2 (&a)[KA], int na,
+                                               const double2 (&b)[KB], int nb) {
+    double mina = a[0].x * nx + a[0].y * ny, maxa = mina;
+#pragma unroll
+    for (int i = 1; i < KA; ++i)
+        if (i < na) {
+            const double p = a[i].x * nx + a[i].y * ny;
+            mina = p < mina ? p : mina;
+            maxa = p > maxa ? p : maxa;
+        }
+    double minb = b[0].x * nx + b[0].y * ny, maxb = minb;
+#pragma unroll
+    for (int i = 1; i < KB; ++i)
+        if (i < nb) {
+            const double p = b[i].x * nx + b[i].y * ny;
+            minb = p < minb ? p : minb;
+            maxb = p > maxb ? p : maxb;
+        }
+    return !(maxa > minb && maxb > mina);
+}
+
+// all edge normals are evaluated (no per-lane early exit): 63 % of the
+// candidate pairs intersect and need every axis anyway
+template <int KA, int KB>
+__device__ __forceinline__ bool polygons_intersect_uniform(const double2 (&a)[KA], int na,
+                                                           const double2 (&b)[KB], int nb) {
+    bool separated = false;
+    double2 p = last_vertex(a, na);
+#pragma unroll
+    for (int i = 0; i < KA; ++i)
+        if (i < na) {
+            const double2 q = a[i];
+            const double nx = -(q.y - p.y), ny = q.x - p.x;
+            p = q;
+            const bool sep = axis_separates(nx, ny, a, na, b, nb);
+            separated |= sep && !(nx == 0.0 && ny == 0.0);
+        }
+    p = last_vertex(b, nb);
+#pragma unroll
+    for (int i = 0; i < KB; ++i)
+        if (i < nb) {
+            const double2 q = b[i];
+            const double nx = -(q.y - p.y), ny = q.x - p.x;
+            p = q;
+            const bool sep = axis_separates(nx, ny, a, na, b, nb);
+            separated |= sep && !(nx == 0.0 && ny == 0.0);
+        }
+    return !separated;
+}
+
+// Each clip stage runs as
+//   pass 1  walk the subject once: drop repeated vertices, evaluate `inside`
+//           for every kept vertex, remember where the in/out state flips
+//           (a convex subject flips 0 or 2 times)
+//   pass 2  compute the (at most two) intersection points -- the only
+//           divisions -- for all lanes together
+//   pass 3  emit [intersection, vertex-if-inside] in subject order
+// instead of interleaving an inside test with a rare, division-heavy
+// intersection per vertex.  Configurations the fast path does not cover (more
+// than two flips, or an intersection with a zero denominator, which alters
+// the state the sequential loop carries) set *fallback; the caller re-runs
+// clip_area() for that lane.
+template <int KT, int KS>
+__device__ __forceinline__ double clip_area_dense(const double2 (&poly)[KT], int np,
+                                                  const double2 (&clip)[KS], int nc, double2 *bufA,
+                                                  double2 *bufB, int stride, bool *fallback) {
+    constexpr int M = KT + KS;
+    double2 *out = bufA, *sub = bufB;
+    int n_out = np;
+#pragma unroll
+    for (int i = 0; i < KT; ++i)
+        if (i < np) out[i * stride] = poly[i];
+
+    bool dead = false;  // fewer than 3 vertices left: area 0
+    bool fb = false;
+    double2 r = last_vertex(clip, nc);
+#pragma unroll
+    for (int i = 0; i < KS; ++i) {
+        const double2 s = clip[i];
+        const double Ux = s.x - r.x, Uy = s.y - r.y;
+        const bool run = (i < nc) && !(Ux == 0.0 && Uy == 0.0) && !dead && !fb;
+        if (run) {
+            const double Nx = -Uy, Ny = Ux;
+            double2 *t = sub;
+            sub = out;
+            out = t;
+            const int length = n_out;
+            // ---- pass 1
+            double2 a = sub[(length - 1) * stride];
+            bool a_in = Ux * (a.y - r.y) > Uy * (a.x - r.x);
+            int a_idx = length - 1;
+            unsigned kept = 0u, inm = 0u;
+            int nflip = 0, cj0 = -1, cp0 = 0, cj1 = -1, cp1 = 0;
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                if (j < length) {
+                    const double2 b = sub[j * stride];
+                    const bool use = !(b.x == a.x && b.y == a.y);
+                    const bool b_in = Ux * (b.y - r.y) > Uy * (b.x - r.x);
+                    const bool flip = use && (b_in != a_in);
+                    const bool first = flip && nflip == 0;
+                    const bool later = flip && nflip != 0;
+                    cj0 = first ? j : cj0;
+                    cp0 = first ? a_idx : cp0;
+                    cj1 = later ? j : cj1;
+                    cp1 = later ? a_idx : cp1;
+                    nflip += flip ? 1 : 0;
+                    kept |= (use ? 1u : 0u) << j;
+                    inm |= ((use && b_in) ? 1u : 0u) << j;
+                    a.x = use ? b.x : a.x;
+                    a.y = use ? b.y : a.y;
+                    a_in = use ? b_in : a_in;
+                    a_idx = use ? j : a_idx;
+                }
+            }
+            fb = fb || nflip > 2;
+            // ---- pass 2
+            double2 X0 = make_double2(0.0, 0.0), X1 = X0;
+            if (nflip > 0) {
+                const double2 pa = sub[cp0 * stride], pb = sub[cj0 * stride];
+                const double Vx = pb.x - pa.x, Vy = pb.y - pa.y;
+                const double Wx = pa.x - r.x, Wy = pa.y - r.y;
+                const double nw = Nx * Wx + Ny * Wy;
+                const double nv = Nx * Vx + Ny * Vy;
+                fb = fb || nv == 0.0;
+                const double tt = -nw / nv;
+                X0 = make_double2(pa.x + tt * Vx, pa.y + tt * Vy);
+            }
+            if (nflip > 1) {
+                const double2 pa = sub[cp1 * stride], pb = sub[cj1 * stride];
+                const double Vx = pb.x - pa.x, Vy = pb.y - pa.y;
+                const double Wx = pa.x - r.x, Wy = pa.y - r.y;
+                const double nw = Nx * Wx + Ny * Wy;
+                const double nv = Nx * Vx + Ny * Vy;
+                fb = fb || nv == 0.0;
+                const double tt = -nw / nv;
+                X1 = make_double2(pa.x + tt * Vx, pa.y + tt * Vy);
+            }
+            // ---- pass 3
+            n_out = 0;
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                if (j < length && ((kept >> j) & 1u)) {
+                    if (j == cj0) { out[n_out * stride] = X0; ++n_out; }
+                    else if (j == cj1) { out[n_out * stride] = X1; ++n_out; }
+                    if ((inm >> j) & 1u) { out[n_out * stride] = sub[j * stride]; ++n_out; }
+                }
+            }
+            dead = n_out < 3;
+            r = s;
+        }
+    }
+    *fallback = fb;
+    if (dead || fb) return 0.0;
+    double area = 0.0;
+    const double2 a0 = out[0];
+    const double2 b0 = out[stride];
+    double Ux = b0.x - a0.x, Uy = b0.y - a0.y;
+#pragma unroll
+    for (int i = 2; i < M; ++i) {
+        if (i < n_out) {
+            const double2 c = out[i * stride];
+            const double Vx = a0.x - c.x, Vy = a0.y - c.y;
+            area += fabs(cross2(Ux, Uy, Vx, Vy));
+            Ux = Vx;
+            Uy = Vy;
+        }
+    }
+    return 0.5 * area;
+}
+
 // on-edge criterion: perpendicular distance to the edge line below `tol`,
 // evaluated as cross^2 < tol^2 * |edge|^2 (tol2 = tol * tol)
 __device__ __forceinline__ bool near_edge(double twice_area, double wx, double wy, double tol2) {

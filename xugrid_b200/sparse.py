@@ -139,12 +139,15 @@ def csr_apply(
     rows = A.n if row_end is None else row_end - row_begin
     if out is None:
         out = torch.empty((n_extra, rows), dtype=torch.float64, device=source.device)
+    if not out.is_cuda or out.dtype != torch.float64 or (rows > 1 and out.stride(1) != 1):
+        raise _native.XgError("out must be a float64 CUDA tensor with unit stride along the rows")
     with torch.cuda.device(source.device):
         _native.check(
             L.xg_csr_apply(
                 code, float(percentile), _native.ptr(A.indptr), _native.ptr(A.indices),
-                _native.ptr(A.data), _native.ptr(source), n_extra, m, rows, _native.ptr(out),
-                int(out.stride(0)), _native.stream_ptr(),
+                _native.ptr(A.data), _native.ptr(source), n_extra, m, rows, out.data_ptr(),
+                int(out.stride(0)) if n_extra > 1 else max(rows, int(out.stride(0))),
+                _native.stream_ptr(),
             )
         )
     return out
