@@ -235,18 +235,23 @@ k_emit(const int64_t *__restrict__ cand_ptr, const int32_t *__restrict__ cand_sr
     }
 }
 
-// Persistent two-phase clipping kernel (the dominant kernel of the build).
-// A block walks chunks of CLIP_T * CLIP_PPT candidate pairs:
-//   phase A  one thread per pair: separating-axis filter.  Rejected pairs get
-//            area 0; survivors are appended to a block-level queue in shared
-//            memory (warp-aggregated: one shared atomic per warp).
-//   phase B  the queue is drained in FULL batches of CLIP_T pairs, one pair
-//            per thread, with clip_area_dense(): every lane clips a pair that
-//            really intersects, so the fp64 pipe sees dense warps.  The
-//            remainder (< CLIP_T pairs) stays queued for the next chunk.
+// Clipping as two dense kernels (the dominant cost of the build).
+//   k_sat   one thread per candidate pair: separating-axis filter, straight-line
+//           code.  Rejected pairs get area 0; survivors are appended to a
+//           compact list as 16-byte records {pair index, target, source}
+//           (block-aggregated: one global atomic per block of 256 pairs, so a
+//           block's survivors stay contiguous and neighbours in space).
+//   k_clip_survivors  one thread per survivor: every lane of a warp clips a
+//           pair that really intersects (clip_area_dense), so the fp64 pipe
+//           sees full warps and no lane idles through another lane's early out.
+// The survivor count stays on the device: k_clip_survivors is launched over
+// the candidate count and surplus threads exit after reading the counter.
 constexpr int CLIP_T = 256;
-constexpr int CLIP_PPT = 3;
-constexpr int CLIP_MIN_BLOCKS = 3;
+
+struct __align__(16) Survivor {
+    int64_t pair;
+    int32_t tgt, src;
+};
 
 // rare slow path of clip_area_dense(), kept out of line so that it does not
 // cost the main path registers
@@ -262,88 +267,78 @@ __device__ __noinline__ double clip_area_fallback(const double2 *pa, int na, con
 }
 
 template <int KT, int KS>
-__global__ void __launch_bounds__(CLIP_T, CLIP_MIN_BLOCKS)
-k_clip_dense(const int32_t *__restrict__ cand_tgt, const int32_t *__restrict__ cand_src,
-             int64_t n_pairs, const double2 *__restrict__ tpoly, const uint8_t *__restrict__ tnv,
-             int kt, const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks,
-             double *__restrict__ area, unsigned long long *__restrict__ stats) {
-    extern __shared__ double2 s_buf[];
-    __shared__ int64_t s_q[CLIP_T * (CLIP_PPT + 1)];
-    __shared__ int s_n;
+__global__ void __launch_bounds__(CLIP_T)
+k_sat(const int32_t *__restrict__ cand_tgt, const int32_t *__restrict__ cand_src, int64_t n_pairs,
+      const double2 *__restrict__ tpoly, const uint8_t *__restrict__ tnv, int kt,
+      const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks,
+      double *__restrict__ area, Survivor *__restrict__ surv, unsigned long long *__restrict__ stats) {
+    __shared__ int s_cnt;
+    __shared__ unsigned long long s_base;
     const int tid = threadIdx.x, lane = tid & 31;
-    double2 *bufA = s_buf + tid;
-    double2 *bufB = s_buf + (size_t)(KT + KS) * CLIP_T + tid;
-    const int64_t chunk_pairs = (int64_t)CLIP_T * CLIP_PPT;
-    const int64_t n_chunks = (n_pairs + chunk_pairs - 1) / chunk_pairs;
-    if (tid == 0) s_n = 0;
+    if (tid == 0) s_cnt = 0;
     __syncthreads();
-    unsigned long long reached = 0;
-
-    auto clip_one = [&](int64_t p) {
+    const int64_t p = blockIdx.x * (int64_t)CLIP_T + tid;
+    bool pass = false;
+    int32_t t = 0, s = 0;
+    if (p < n_pairs) {
+        t = cand_tgt[p];
+        s = cand_src[p];
         double2 a[KT], b[KS];
-        const int na = load_poly<KT>(tpoly, tnv, cand_tgt[p], kt, a);
-        const int nb = load_poly<KS>(spoly, snv, cand_src[p], ks, b);
-        bool fb = false;
-        double ar = clip_area_dense<KT, KS>(a, na, b, nb, bufA, bufB, CLIP_T, &fb);
-        if (fb) ar = clip_area_fallback<KT, KS>(a, na, b, nb, bufA, bufB, CLIP_T);
-        area[p] = ar;
-    };
-
-    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const int64_t base = chunk * chunk_pairs;
-#pragma unroll 1
-        for (int i = 0; i < CLIP_PPT; ++i) {
-            const int64_t p = base + (int64_t)i * CLIP_T + tid;
-            bool pass = false;
-            if (p < n_pairs) {
-                double2 a[KT], b[KS];
-                const int na = load_poly<KT>(tpoly, tnv, cand_tgt[p], kt, a);
-                const int nb = load_poly<KS>(spoly, snv, cand_src[p], ks, b);
-                pass = polygons_intersect_uniform<KT, KS>(a, na, b, nb);
-                if (!pass) area[p] = 0.0;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                int pos = 0;
-                if (lane == __ffs(m) - 1) pos = atomicAdd(&s_n, __popc(m));
-                pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1);
-                if (pass) s_q[pos + __popc(m & ((1u << lane) - 1u))] = p;
-            }
-        }
-        __syncthreads();
-        const int n = s_n;
-        const int full = (n / CLIP_T) * CLIP_T;
-        for (int q = tid; q < full; q += CLIP_T) clip_one(s_q[q]);
-        reached += (unsigned long long)(full / CLIP_T);
-        __syncthreads();
-        const int rest = n - full;
-        int64_t keep = 0;
-        if (tid < rest) keep = s_q[full + tid];
-        __syncthreads();
-        if (tid < rest) s_q[tid] = keep;
-        if (tid == 0) s_n = rest;
-        __syncthreads();
+        const int na = load_poly<KT>(tpoly, tnv, t, kt, a);
+        const int nb = load_poly<KS>(spoly, snv, s, ks, b);
+        pass = polygons_intersect_uniform<KT, KS>(a, na, b, nb);
+        if (!pass) area[p] = 0.0;
     }
-    const int rest = s_n;
-    if (tid < rest) clip_one(s_q[tid]);
-    if (stats && tid == 0) atomicAdd(stats + 3, reached * CLIP_T + (unsigned long long)rest);
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    int pos = 0;
+    if (m) {
+        if (lane == __ffs(m) - 1) pos = atomicAdd(&s_cnt, __popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    if (tid == 0 && s_cnt > 0) s_base = atomicAdd(stats + 3, (unsigned long long)s_cnt);
+    __syncthreads();
+    if (pass) {
+        Survivor r;
+        r.pair = p; r.tgt = t; r.src = s;
+        surv[s_base + pos] = r;
+    }
+}
+
+template <int KT, int KS>
+__global__ void __launch_bounds__(CLIP_T, 3)
+k_clip_survivors(const Survivor *__restrict__ surv, const unsigned long long *__restrict__ n_surv,
+                 const double2 *__restrict__ tpoly, const uint8_t *__restrict__ tnv, int kt,
+                 const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks,
+                 double *__restrict__ area) {
+    extern __shared__ double2 s_buf[];
+    const int64_t q = blockIdx.x * (int64_t)CLIP_T + threadIdx.x;
+    if (q >= (int64_t)*n_surv) return;
+    const Survivor r = surv[q];
+    double2 *bufA = s_buf + threadIdx.x;
+    double2 *bufB = s_buf + (size_t)(KT + KS) * CLIP_T + threadIdx.x;
+    double2 a[KT], b[KS];
+    const int na = load_poly<KT>(tpoly, tnv, r.tgt, kt, a);
+    const int nb = load_poly<KS>(spoly, snv, r.src, ks, b);
+    bool fb = false;
+    double ar = clip_area_dense<KT, KS>(a, na, b, nb, bufA, bufB, CLIP_T, &fb);
+    if (fb) ar = clip_area_fallback<KT, KS>(a, na, b, nb, bufA, bufB, CLIP_T);
+    area[r.pair] = ar;
 }
 
 template <int KT, int KS>
 static int launch_clip_dense(const int32_t *ct, const int32_t *cs, int64_t n_pairs,
                              const double *tpoly, const uint8_t *tnv, int kt, const double *spoly,
-                             const uint8_t *snv, int ks, double *area, unsigned long long *stats,
-                             cudaStream_t s) {
+                             const uint8_t *snv, int ks, double *area, void *surv,
+                             unsigned long long *stats, cudaStream_t s) {
+    const unsigned grid = (unsigned)div_up(n_pairs, CLIP_T);
+    k_sat<KT, KS><<<grid, CLIP_T, 0, s>>>(ct, cs, n_pairs, (const double2 *)tpoly, tnv, kt,
+                                          (const double2 *)spoly, snv, ks, area, (Survivor *)surv, stats);
+    XG_CHECK_LAUNCH();
     const size_t smem = sizeof(double2) * 2 * (size_t)(KT + KS) * CLIP_T;
-    XG_CUDA(cudaFuncSetAttribute(k_clip_dense<KT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip_dense<KT, KS>, CLIP_T, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int64_t n_chunks = div_up(n_pairs, (int64_t)CLIP_T * CLIP_PPT);
-    int64_t grid = (int64_t)NUM_SMS * per_sm;
-    if (grid > n_chunks) grid = n_chunks;
-    k_clip_dense<KT, KS><<<(unsigned)grid, CLIP_T, smem, s>>>(
-        ct, cs, n_pairs, (const double2 *)tpoly, tnv, kt, (const double2 *)spoly, snv, ks, area, stats);
+    XG_CUDA(cudaFuncSetAttribute(k_clip_survivors<KT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_clip_survivors<KT, KS><<<grid, CLIP_T, smem, s>>>((const Survivor *)surv, stats + 3, (const double2 *)tpoly, tnv, kt,
+                                                        (const double2 *)spoly, snv, ks, area);
     XG_CHECK_LAUNCH();
     return XG_OK;
 }
@@ -488,11 +483,13 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
             const uint8_t *tnv = job->tnv.as<uint8_t>();
             unsigned long long *st = job->stats.as<unsigned long long>();
             double *ar = job->area.as<double>();
-            if (k_t == 3 && ks == 3) rc = launch_clip_dense<3, 3>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, st, s);
-            else if (k_t == 3 && ks == 4) rc = launch_clip_dense<3, 4>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, st, s);
-            else if (k_t == 4 && ks == 3) rc = launch_clip_dense<4, 3>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, st, s);
-            else if (k_t == 4 && ks == 4) rc = launch_clip_dense<4, 4>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, st, s);
-            else if (k_t <= 8 && ks <= 8) rc = launch_clip_dense<8, 8>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, st, s);
+            DevBuf surv;  // compact list of pairs that pass the separating-axis filter
+            if (k_t <= 8 && ks <= 8) OV_CUDA(surv.alloc(sizeof(Survivor) * (size_t)n_cand, s));
+            if (k_t == 3 && ks == 3) rc = launch_clip_dense<3, 3>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, surv.p, st, s);
+            else if (k_t == 3 && ks == 4) rc = launch_clip_dense<3, 4>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, surv.p, st, s);
+            else if (k_t == 4 && ks == 3) rc = launch_clip_dense<4, 3>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, surv.p, st, s);
+            else if (k_t == 4 && ks == 4) rc = launch_clip_dense<4, 4>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, surv.p, st, s);
+            else if (k_t <= 8 && ks <= 8) rc = launch_clip_dense<8, 8>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, surv.p, st, s);
             else rc = launch_clip<XG_MAX_N_VERTEX, XG_MAX_N_VERTEX>(32, ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, st, s);
             if (rc) goto fail;
         }
