@@ -12,7 +12,7 @@ apply of `mean` + (N > 1) the all-gather that reassembles the output.
  * value : whole-job target faces/s with the meshes already resident in HBM
  * e2e   : the same step through the public API with HOST (pinned) buffers:
            H2D of both meshes and the values, compute, D2H of the result
- * roofline    : the dominant kernel (k_clip), algorithmic bytes / its measured time
+ * roofline    : the dominant kernel (k_clip_survivors), algorithmic bytes / its measured time
  * cpu_baseline: the CPU oracle (C/OpenMP restatement of the reference's path)
                  on a bounded sample of the same workload, N = 1 only
  * --impl reference: the oracle port on all host threads (the reference is
@@ -233,7 +233,7 @@ def run_ours(args) -> int:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("XG_BENCH_NO_SMI")) else None
     ms_dev = timed(lambda: step(d), args.steps, args.warmup)
     # per-phase device times of the last resident step (CUDA events inside the library)
     phases = dict(state["tree"].last_phase_ms)
@@ -260,9 +260,10 @@ def run_ours(args) -> int:
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         k_t = k_s = 3
-        # dominant kernel k_clip: per candidate pair it reads the pair ids (8 B) and both
-        # polygons (k*16 B each) and writes one area (8 B)  -- DESIGN.md section 5
-        clip_bytes = stats.candidates * (8 + 16 * k_t + 16 * k_s + 8)
+        # dominant kernel k_clip_survivors: per surviving pair it reads the pair ids (8 B) and
+        # both polygons (k*16 B each), writes one area (8 B) and bumps one row counter (4 B)
+        # -- DESIGN.md section 5
+        clip_bytes = stats.clip_pairs * (8 + 16 * k_t + 16 * k_s + 8 + 4)
         clip_ms = phases.get("clip", float("nan"))
         achieved = clip_bytes / (clip_ms * 1e-3) / 1e9 if clip_ms and clip_ms > 0 else None
         # SURVEY 8(d) gather model for the whole build of this rank's rows
@@ -288,12 +289,12 @@ def run_ours(args) -> int:
                 "workload": workload_name(args.n_side), "n_source_faces": n_s, "n_target_faces": n_t,
                 "nnz": stats.nnz if world == 1 else None, "sharding": f"target rows [{b},{e}) on rank 0 of {world}",
                 "l2": "inputs (2 x 320 MB meshes + 1.5 GB packed records) exceed the 126 MB L2; no explicit flush",
-                "cub_launches_per_step": 22,
+                "cub_launches_per_step": 14,
             },
             "e2e": {"value": n_t / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": 6 + n_levels + 7 + 1,
-            "roofline": {"bound": "hbm", "kernel": "k_clip<3,3>", "achieved": achieved, "peak": peak,
+            "gpu_launches": 6 + n_levels + 8 + 1,
+            "roofline": {"bound": "hbm", "kernel": "k_clip_survivors<3,3>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes": clip_bytes, "ms": clip_ms,
                          "note": "fp64/issue-bound clipping kernel; see DESIGN.md section 5"},

@@ -68,6 +68,10 @@ typedef struct xg_overlap xg_overlap;   /* one in-flight overlap job */
 
 int xg_abi_version(void);
 const char *xg_last_error_string(void);
+/* The library keeps released scratch blocks and index arenas for re-use by the
+ * next call of similar size (same device, same stream).  This returns them to
+ * the driver (synchronises the device). */
+int xg_release_cached_memory(void);
 
 /* ---- spatial index -------------------------------------------------------
  * Replaces numba_celltree.CellTree2d(vertices, faces, fill_value) as built by
@@ -105,21 +109,21 @@ int xg_overlap_begin(const xg_index *source, const double *d_t_xy, int64_t n_t_n
 int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32_t *d_indices,
                       double *d_area, int relative, void *stream);
 /* counters of the job for the byte model:
- * stats[0]=targets stats[1]=tree-node visits (V) stats[2]=leaf bbox tests (C)
- * stats[3]=pairs that reached the clipper (C_clip) stats[4]=nnz
+ * stats[0]=targets stats[1]=wide-node visits (V, one coalesced load of <= 32
+ * boxes each) stats[2]=leaf bbox tests (C) stats[3]=pairs that passed the
+ * separating-axis filter and reached the clipper (C_clip) stats[4]=nnz
  * stats[5]=bbox candidates.  Valid after xg_overlap_begin. */
 int xg_overlap_stats(const xg_overlap *job, int64_t stats[8]);
 /* device time of each phase of xg_overlap_begin in milliseconds (CUDA events on
  * the job's stream), indexed by xg_phase.  Valid after xg_overlap_begin. */
 typedef enum xg_phase {
-    XG_PHASE_PACK = 0,    /* Morton order + packing of the target faces */
-    XG_PHASE_COUNT = 1,   /* BVH walk, candidate count per target */
-    XG_PHASE_SCAN = 2,    /* candidate row pointer (+ size read-back) */
-    XG_PHASE_FILL = 3,    /* BVH walk, candidate write */
-    XG_PHASE_CLIP = 4,    /* separating-axis filter + Sutherland-Hodgman area */
-    XG_PHASE_ROWPTR = 5   /* positives per row + CSR row pointer */
+    XG_PHASE_PACK = 0,      /* Morton order + packing of the target faces */
+    XG_PHASE_TRAVERSE = 1,  /* BVH walk -> candidate pairs */
+    XG_PHASE_SAT = 2,       /* separating-axis filter -> survivors */
+    XG_PHASE_CLIP = 3,      /* Sutherland-Hodgman area of the survivors */
+    XG_PHASE_ROWPTR = 4     /* CSR row pointer (+ size read-back) */
 } xg_phase;
-#define XG_N_PHASES 6
+#define XG_N_PHASES 5
 int xg_overlap_timings(const xg_overlap *job, double ms[8]);
 int xg_overlap_abort(xg_overlap *job);
 

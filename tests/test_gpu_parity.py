@@ -364,3 +364,18 @@ def test_full_size_properties(xb):
     assert np.array_equal(np.repeat(np.arange(e - b), np.diff(ip)), oti)
     assert np.array_equal(indices[ip[0] : ip[-1]].cpu().numpy(), osi)
     assert np.array_equal(area[ip[0] : ip[-1]].cpu().numpy(), oa)
+
+
+def test_overlap_dense_sources_rerun_path(xb):
+    """~130 candidates per target: more than the arena guess (16 per target), so
+    the walk is re-run with the exact size it counted; also rows longer than the
+    8-entry register sort."""
+    sxy, sf = synthetic.jittered_lattice(160, 160, 21, "tri")
+    txy, tf = synthetic.jittered_lattice(20, 20, 22, "mixed", bounds=(0.03, 0.97, 0.03, 0.97))
+    g, tree = gpu_triplets(xb, sxy, sf, txy, tf)
+    assert tree.last_stats.candidates > 16 * len(tf)
+    assert_same_triplets(g, oracle_triplets(sxy, sf, txy, tf))
+    indptr, indices, _ = (t.cpu().numpy() for t in tree.intersect_faces_csr(txy, tf))
+    assert np.diff(indptr).max() > 8
+    rows = np.repeat(np.arange(len(tf)), np.diff(indptr))
+    assert np.array_equal(np.lexsort((indices, rows)), np.arange(len(indices)))

@@ -26,6 +26,7 @@ _dbl = ctypes.c_double
 SIGNATURES = {
     "xg_abi_version": (_int, []),
     "xg_last_error_string": (ctypes.c_char_p, []),
+    "xg_release_cached_memory": (_int, []),
     "xg_index_create": (_int, [_vp, _i64, _vp, _int, _i64, _int, _vp, ctypes.POINTER(_vp)]),
     "xg_index_destroy": (_int, [_vp]),
     "xg_index_info": (_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_dbl)]),

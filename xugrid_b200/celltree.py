@@ -69,7 +69,7 @@ def faces_to_device(faces: ArrayLike, fill_value: int, device: torch.device) -> 
     return t
 
 
-PHASES = ("pack", "count", "scan", "fill", "clip", "rowptr")
+PHASES = ("pack", "traverse", "sat", "clip", "rowptr")
 
 
 class OverlapStats(NamedTuple):

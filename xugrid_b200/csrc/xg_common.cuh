@@ -37,11 +37,21 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Device memory for scratch buffers and index arenas comes from a small block
+// cache in front of cudaMallocAsync: a released block is kept and handed to the
+// next request of a similar size on the same stream.  Re-use is safe because
+// all work is stream-ordered; it matters because a regridder is rebuilt with
+// the same sizes over and over, and asking the driver's pool for several GB
+// per call stalls the stream for milliseconds whenever no device-wide
+// synchronisation happened since the last free (measured: 0.8 ms -> 7 ms).
+cudaError_t scratch_alloc(void **p, size_t *cap, size_t bytes, cudaStream_t s);
+void scratch_free(void *p, size_t cap, cudaStream_t s);
+
 // stream-ordered scratch allocation that frees itself
 struct DevBuf {
     void *p = nullptr;
     cudaStream_t s = nullptr;
-    size_t bytes = 0;
+    size_t bytes = 0, cap = 0;
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -50,10 +60,10 @@ struct DevBuf {
         release();
         s = stream;
         bytes = n ? n : 16;
-        return cudaMallocAsync(&p, bytes, stream);
+        return scratch_alloc(&p, &cap, bytes, stream);
     }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p) scratch_free(p, cap, s);
         p = nullptr;
     }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
@@ -76,6 +86,8 @@ struct xg_index {
     double bounds[4];                 // xmin, xmax, ymin, ymax of the mesh
     double default_tolerance = 0.0;   // 1e-12 * max bbox diagonal
     size_t bytes = 0;
+    size_t arena_cap = 0;
+    cudaStream_t arena_stream = nullptr;
     void *arena = nullptr;            // single device allocation backing all arrays
     double *d_frame = nullptr;        // device copy of bounds[4] + default tolerance
 };

@@ -16,6 +16,9 @@
 //      is entry 32*p + j of level l-1                           (k_reduce_level)
 #include <cub/device/device_radix_sort.cuh>
 
+#include <mutex>
+#include <vector>
+
 #include "xg_common.cuh"
 #include "xg_pack.cuh"
 
@@ -35,6 +38,69 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     set_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e),
               file, line, what);
     return XG_ERR_CUDA;
+}
+
+// ---- block cache (see xg_common.cuh) ----------------------------------------------
+struct CachedBlock {
+    void *p;
+    size_t cap;
+    cudaStream_t s;
+    int dev;
+};
+static std::mutex g_cache_mutex;
+static std::vector<CachedBlock> g_cache;
+static size_t g_cached_bytes = 0;
+static const size_t g_cache_limit = (size_t)96 << 30;
+
+static size_t round_size(size_t n) {
+    const size_t g = n >= ((size_t)2 << 20) ? ((size_t)2 << 20) : 512;
+    return (n + g - 1) / g * g;
+}
+
+cudaError_t scratch_alloc(void **p, size_t *cap, size_t bytes, cudaStream_t s) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t want = round_size(bytes);
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        int best = -1;
+        for (int i = 0; i < (int)g_cache.size(); ++i) {
+            const CachedBlock &b = g_cache[i];
+            if (b.dev != dev || b.s != s || b.cap < want || b.cap > want + want / 2 + ((size_t)1 << 20)) continue;
+            if (best < 0 || b.cap < g_cache[best].cap) best = i;
+        }
+        if (best >= 0) {
+            *p = g_cache[best].p;
+            *cap = g_cache[best].cap;
+            g_cached_bytes -= g_cache[best].cap;
+            g_cache[best] = g_cache.back();
+            g_cache.pop_back();
+            return cudaSuccess;
+        }
+    }
+    *cap = want;
+    return cudaMallocAsync(p, want, s);
+}
+
+void scratch_free(void *p, size_t cap, cudaStream_t s) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        if (g_cached_bytes + cap <= g_cache_limit) {
+            g_cache.push_back(CachedBlock{p, cap, s, dev});
+            g_cached_bytes += cap;
+            return;
+        }
+    }
+    cudaFreeAsync(p, s);
+}
+
+static void release_cache() {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    for (const CachedBlock &b : g_cache) cudaFreeAsync(b.p, b.s);
+    g_cache.clear();
+    g_cached_bytes = 0;
 }
 
 // ---- kernels ------------------------------------------------------------------
@@ -372,8 +438,9 @@ extern "C" int xg_index_create(const double *d_xy, int64_t n_node, const void *d
     const size_t off_frame = off; off = align_up(off + sizeof(double) * 8, 256);
     const size_t off_red = off; off = align_up(off + sizeof(unsigned long long) * 8, 256);
     ix->bytes = off;
-    cudaError_t e = cudaMallocAsync(&ix->arena, off, s);
-    if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMallocAsync(index)", __FILE__, __LINE__); }
+    ix->arena_stream = s;
+    cudaError_t e = scratch_alloc(&ix->arena, &ix->arena_cap, off, s);
+    if (e != cudaSuccess) { delete ix; return cuda_fail(e, "scratch_alloc(index)", __FILE__, __LINE__); }
     char *base = (char *)ix->arena;
     ix->leaf_box = (Box *)(base + off_box);
     for (int l = 0; l < n_levels; ++l) { ix->level_box[l] = (Box *)(base + off_lvl[l]); ix->level_n[l] = level_n[l]; }
@@ -414,7 +481,7 @@ extern "C" int xg_index_create(const double *d_xy, int64_t n_node, const void *d
         ix->default_tolerance = h[4];
     } while (0);
     if (rc) {
-        cudaFreeAsync(ix->arena, s);
+        scratch_free(ix->arena, ix->arena_cap, s);
         delete ix;
         return rc;
     }
@@ -424,8 +491,18 @@ extern "C" int xg_index_create(const double *d_xy, int64_t n_node, const void *d
 
 extern "C" int xg_index_destroy(xg_index *ix) {
     if (!ix) return XG_OK;
-    if (ix->arena) cudaFree(ix->arena);
+    if (ix->arena) {
+        // queries may have been enqueued on other streams than the creation stream
+        cudaDeviceSynchronize();
+        scratch_free(ix->arena, ix->arena_cap, ix->arena_stream);
+    }
     delete ix;
+    return XG_OK;
+}
+
+extern "C" int xg_release_cached_memory(void) {
+    cudaDeviceSynchronize();
+    xg::release_cache();
     return XG_OK;
 }
 

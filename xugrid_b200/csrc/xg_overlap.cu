@@ -6,18 +6,24 @@
 // Sutherland-Hodgman area -> keep area > 0) and MatrixCSR.from_triplet
 // (/root/reference/xugrid/core/sparse.py:61-78,119-127).
 //
-// Pipeline (all on the caller's stream):
-//   pack_mesh(targets)            targets in Morton order, self-contained records
-//   k_traverse<false>             one warp walks the wide BVH for a TILE of 32
-//                                 Morton-consecutive targets (lane = target):
-//                                 child boxes are loaded once per warp, coalesced,
-//                                 and tested by all lanes from shared memory;
-//                                 hit masks are combined with warp votes
-//   cub ExclusiveSum              candidate row pointer
-//   k_traverse<true>              same walk, writes (target, source) candidates
-//   k_clip                        one thread per candidate: SAT + clip area (fp64)
-//   k_row_count + cub ExclusiveSum  CSR row pointer in the caller's row order
-//   k_emit (xg_overlap_finish)    rows written in ascending source index
+// Pipeline (all on the caller's stream, ONE host synchronisation at the end):
+//   pack_mesh(targets)   targets in Morton order, self-contained records
+//   k_traverse           one warp walks the wide BVH ONCE for a tile of 32
+//                        Morton-consecutive targets (lane = target).  Child
+//                        boxes are loaded once per warp, coalesced, and tested
+//                        by all lanes from shared memory; hits are compacted
+//                        with warp votes into a per-warp queue that is flushed
+//                        to a global pair arena (one atomic per ~100 pairs)
+//   k_sat                one thread per candidate pair: separating-axis filter;
+//                        survivors appended to a dense list
+//   k_clip_survivors     one thread per survivor: Sutherland-Hodgman area,
+//                        warp-uniform code; positive areas bump their row count
+//   cub ExclusiveSum     CSR row pointer in the caller's row order
+//   k_scatter + k_sort_rows (xg_overlap_finish)  entries dropped into their
+//                        rows, every row ordered by ascending source index
+// The arena is sized from a density guess (16 candidates per target); if the
+// walk finds more, the job is re-run once with the exact size the first walk
+// counted (the reference always walks twice: count pass + fill pass).
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
@@ -29,6 +35,12 @@ namespace xg {
 
 constexpr int TRAV_WARPS = 8;
 constexpr int TRAV_STACK = 256;
+constexpr int TRAV_QCAP = 128;    // pair queue entries per warp
+constexpr int TRAV_QFLUSH = 96;   // flush threshold (a child test adds <= 32)
+constexpr int PAIRS_PER_TARGET_GUESS = 16;
+
+// device counters of one job
+enum { CTR_VISITS = 0, CTR_TESTS = 1, CTR_PAIRS = 2, CTR_SURV = 3, CTR_N = 8 };
 
 struct TraverseParams {
     const Box *boxes[MAX_LEVELS + 1];  // [0] = leaves, [d] = node level d-1
@@ -41,17 +53,15 @@ __device__ __forceinline__ bool boxes_intersect(const Box &a, const Box &b) {
     return a.xmin < b.xmax && b.xmin < a.xmax && a.ymin < b.ymax && b.ymin < a.ymax;
 }
 
-// stats: [0] node visits (warp-level, each one coalesced load of <= 32 boxes)
-//        [1] exact leaf bbox tests  [2] candidates
-template <bool FILL>
+// pairs[i] = {sorted target position, sorted source position}
 __global__ void __launch_bounds__(TRAV_WARPS * 32)
 k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t,
-           int32_t *__restrict__ cand_cnt, const int64_t *__restrict__ cand_ptr,
-           int32_t *__restrict__ cand_src, int32_t *__restrict__ cand_tgt,
-           unsigned long long *__restrict__ stats) {
+           int2 *__restrict__ pairs, unsigned long long cap, unsigned long long *__restrict__ ctr) {
     __shared__ Box s_node[TRAV_WARPS][32];
     __shared__ int32_t s_stack[TRAV_WARPS][TRAV_STACK];
+    __shared__ int2 s_q[TRAV_WARPS][TRAV_QCAP];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t tile = blockIdx.x * (int64_t)TRAV_WARPS + w;
     const int64_t t = tile * 32 + lane;
     if (tile * 32 >= n_t) return;
@@ -67,12 +77,21 @@ k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t,
         ub.ymin = fmin(ub.ymin, __shfl_xor_sync(0xffffffffu, ub.ymin, o));
         ub.ymax = fmax(ub.ymax, __shfl_xor_sync(0xffffffffu, ub.ymax, o));
     }
-    int sp = 0;
+    int sp = 1, qn = 0;
     if (lane == 0) s_stack[w][0] = P.top << 27;
-    sp = 1;
-    int cnt = 0;
-    const int64_t base = (FILL && valid) ? cand_ptr[t] : 0;
     unsigned visits = 0, tests = 0;
+
+    auto flush = [&]() {
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(ctr + CTR_PAIRS, (unsigned long long)qn);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < qn; i += 32)
+            if (base + i < cap) pairs[base + i] = s_q[w][i];
+        __syncwarp();
+        qn = 0;
+    };
+
     __syncwarp();
     while (sp > 0) {
         const int32_t entry = s_stack[w][--sp];
@@ -105,29 +124,19 @@ k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t,
                 const int c = __ffs(m) - 1;
                 m &= m - 1;
                 const Box b = s_node[w][c];
-                if (boxes_intersect(tb, b)) {
-                    if (FILL) {
-                        cand_src[base + cnt] = (int32_t)(c0 + c);
-                        cand_tgt[base + cnt] = (int32_t)t;
-                    }
-                    ++cnt;
-                }
+                const bool hit = boxes_intersect(tb, b);
+                const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                if (hit) s_q[w][qn + __popc(hm & lt_mask)] = make_int2((int32_t)t, (int32_t)(c0 + c));
+                qn += __popc(hm);
+                if (qn >= TRAV_QFLUSH) flush();
             }
         }
         __syncwarp();
     }
-    if (!FILL) {
-        if (valid) cand_cnt[t] = cnt;
-        if (stats) {
-            unsigned c = cnt;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (lane == 0) {
-                atomicAdd(stats + 0, (unsigned long long)visits);
-                atomicAdd(stats + 1, (unsigned long long)tests * 32ull);
-                atomicAdd(stats + 2, (unsigned long long)c);
-            }
-        }
+    if (qn > 0) flush();
+    if (lane == 0) {
+        atomicAdd(ctr + CTR_VISITS, (unsigned long long)visits);
+        atomicAdd(ctr + CTR_TESTS, (unsigned long long)tests * 32ull);
     }
 }
 
@@ -142,116 +151,14 @@ __device__ __forceinline__ int load_poly(const double2 *__restrict__ poly, const
     return nv[i] & 0x7f;
 }
 
-// one thread per candidate pair: separating-axis filter, then clip area.
-// area[p] = 0 for pairs that do not intersect.
-template <int KT, int KS>
-__global__ void __launch_bounds__(128)
-k_clip(const int32_t *__restrict__ cand_tgt, const int32_t *__restrict__ cand_src, int64_t n_pairs,
-       const double2 *__restrict__ tpoly, const uint8_t *__restrict__ tnv, int kt,
-       const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks,
-       double *__restrict__ area, unsigned long long *__restrict__ stats) {
-    extern __shared__ double2 s_buf[];
-    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int stride = blockDim.x;
-    double2 *bufA = s_buf + threadIdx.x;
-    double2 *bufB = s_buf + (size_t)(KT + KS) * stride + threadIdx.x;
-    bool reached = false;
-    if (p < n_pairs) {
-        double2 a[KT], b[KS];
-        const int na = load_poly<KT>(tpoly, tnv, cand_tgt[p], kt, a);
-        const int nb = load_poly<KS>(spoly, snv, cand_src[p], ks, b);
-        double ar = 0.0;
-        if (polygons_intersect<KT, KS>(a, na, b, nb)) {
-            reached = true;
-            ar = clip_area<KT, KS>(a, na, b, nb, bufA, bufB, stride);
-        }
-        area[p] = ar;
-    }
-    if (stats) {
-        const unsigned m = __ballot_sync(0xffffffffu, reached);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(stats + 3, (unsigned long long)__popc(m));
-    }
-}
-
-// positives per sorted target -> row count at the caller's row position
-__global__ void __launch_bounds__(256)
-k_row_count(const int64_t *__restrict__ cand_ptr, const double *__restrict__ area,
-            const int32_t *__restrict__ tperm, int64_t t_begin, int64_t n_t,
-            int32_t *__restrict__ row_cnt) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n_t) return;
-    int c = 0;
-    for (int64_t p = cand_ptr[i]; p < cand_ptr[i + 1]; ++p) c += area[p] > 0.0;
-    row_cnt[tperm[i] - t_begin] = c;
-}
-
-// area of a packed face with the reference's arithmetic (connectivity.py:615-633:
-// shoelace relative to the first vertex of the ORIGINAL vertex order)
-__device__ __forceinline__ double packed_face_area(const double2 *__restrict__ poly, int k, uint8_t nvf) {
-    const int n = nvf & 0x7f;
-    const bool flip = nvf & 0x80;
-    (void)k;
-    const double2 v0 = poly[flip ? n - 1 : 0];
-    double det = 0.0;
-    for (int j = 0; j < n; ++j) {
-        const int ja = flip ? n - 1 - j : j;
-        const int jn = (j + 1 < n) ? j + 1 : 0;
-        const int jb = flip ? n - 1 - jn : jn;
-        const double ax = poly[ja].x - v0.x, ay = poly[ja].y - v0.y;
-        const double bx = poly[jb].x - v0.x, by = poly[jb].y - v0.y;
-        det += ax * by - ay * bx;
-    }
-    return 0.5 * fabs(det);
-}
-
-// one thread per sorted target: copy its positive pairs into the CSR row and
-// order the row by ascending source face id
-__global__ void __launch_bounds__(256)
-k_emit(const int64_t *__restrict__ cand_ptr, const int32_t *__restrict__ cand_src,
-       const double *__restrict__ area, const int32_t *__restrict__ tperm, int64_t t_begin,
-       int64_t n_t, const int32_t *__restrict__ sperm, const double2 *__restrict__ spoly,
-       const uint8_t *__restrict__ snv, int ks, int relative, const int64_t *__restrict__ indptr,
-       int32_t *__restrict__ indices, double *__restrict__ data) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n_t) return;
-    const int64_t dst = indptr[tperm[i] - t_begin];
-    int n = 0;
-    for (int64_t p = cand_ptr[i]; p < cand_ptr[i + 1]; ++p) {
-        double a = area[p];
-        if (!(a > 0.0)) continue;
-        const int32_t s = cand_src[p];
-        const int32_t sid = sperm[s];
-        if (relative) a = a / packed_face_area(spoly + (int64_t)s * ks, ks, snv[s]);
-        // insertion into the sorted prefix
-        int j = n - 1;
-        while (j >= 0 && indices[dst + j] > sid) {
-            indices[dst + j + 1] = indices[dst + j];
-            data[dst + j + 1] = data[dst + j];
-            --j;
-        }
-        indices[dst + j + 1] = sid;
-        data[dst + j + 1] = a;
-        ++n;
-    }
-}
-
-// Clipping as two dense kernels (the dominant cost of the build).
-//   k_sat   one thread per candidate pair: separating-axis filter, straight-line
-//           code.  Rejected pairs get area 0; survivors are appended to a
-//           compact list as 16-byte records {pair index, target, source}
-//           (block-aggregated: one global atomic per block of 256 pairs, so a
-//           block's survivors stay contiguous and neighbours in space).
-//   k_clip_survivors  one thread per survivor: every lane of a warp clips a
-//           pair that really intersects (clip_area_dense), so the fp64 pipe
-//           sees full warps and no lane idles through another lane's early out.
-// The survivor count stays on the device: k_clip_survivors is launched over
-// the candidate count and surplus threads exit after reading the counter.
-constexpr int CLIP_T = 256;
-
-struct __align__(16) Survivor {
-    int64_t pair;
-    int32_t tgt, src;
-};
+// ---- clipping: two dense kernels (the dominant cost of the build) -----------------
+//   k_sat   one thread per candidate pair, straight-line separating-axis filter;
+//           survivors are appended to a compact list (block-aggregated: one
+//           global atomic per block, so a block's survivors stay contiguous)
+//   k_clip_survivors  one thread per survivor: every lane of a warp clips a pair
+//           that really intersects, so the fp64 pipe sees full warps
+// Both read their element count from device memory and stride over it, so no
+// host round trip separates them from the walk.
 
 // rare slow path of clip_area_dense(), kept out of line so that it does not
 // cost the main path registers
@@ -266,97 +173,216 @@ __device__ __noinline__ double clip_area_fallback(const double2 *pa, int na, con
     return clip_area<KT, KS>(a, na, b, nb, bufA, bufB, stride);
 }
 
-template <int KT, int KS>
-__global__ void __launch_bounds__(CLIP_T)
-k_sat(const int32_t *__restrict__ cand_tgt, const int32_t *__restrict__ cand_src, int64_t n_pairs,
-      const double2 *__restrict__ tpoly, const uint8_t *__restrict__ tnv, int kt,
-      const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks,
-      double *__restrict__ area, Survivor *__restrict__ surv, unsigned long long *__restrict__ stats) {
+template <int KT, int KS, int BT>
+__global__ void __launch_bounds__(BT)
+k_sat(const int2 *__restrict__ pairs, unsigned long long cap, const double2 *__restrict__ tpoly,
+      const uint8_t *__restrict__ tnv, int kt, const double2 *__restrict__ spoly,
+      const uint8_t *__restrict__ snv, int ks, int2 *__restrict__ surv,
+      unsigned long long *__restrict__ ctr) {
     __shared__ int s_cnt;
     __shared__ unsigned long long s_base;
     const int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    const int64_t p = blockIdx.x * (int64_t)CLIP_T + tid;
-    bool pass = false;
-    int32_t t = 0, s = 0;
-    if (p < n_pairs) {
-        t = cand_tgt[p];
-        s = cand_src[p];
-        double2 a[KT], b[KS];
-        const int na = load_poly<KT>(tpoly, tnv, t, kt, a);
-        const int nb = load_poly<KS>(spoly, snv, s, ks, b);
-        pass = polygons_intersect_uniform<KT, KS>(a, na, b, nb);
-        if (!pass) area[p] = 0.0;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, pass);
-    int pos = 0;
-    if (m) {
-        if (lane == __ffs(m) - 1) pos = atomicAdd(&s_cnt, __popc(m));
-        pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
-    }
-    __syncthreads();
-    if (tid == 0 && s_cnt > 0) s_base = atomicAdd(stats + 3, (unsigned long long)s_cnt);
-    __syncthreads();
-    if (pass) {
-        Survivor r;
-        r.pair = p; r.tgt = t; r.src = s;
-        surv[s_base + pos] = r;
+    unsigned long long n_pairs = ctr[CTR_PAIRS];
+    if (n_pairs > cap) n_pairs = cap;  // overflowed walk: the job is re-run anyway
+    for (unsigned long long base = (unsigned long long)blockIdx.x * BT; base < n_pairs;
+         base += (unsigned long long)gridDim.x * BT) {
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        const unsigned long long p = base + tid;
+        bool pass = false;
+        int2 pr = make_int2(0, 0);
+        if (p < n_pairs) {
+            pr = pairs[p];
+            double2 a[KT], b[KS];
+            const int na = load_poly<KT>(tpoly, tnv, pr.x, kt, a);
+            const int nb = load_poly<KS>(spoly, snv, pr.y, ks, b);
+            if (KT <= 8 && KS <= 8) pass = polygons_intersect_uniform<KT, KS>(a, na, b, nb);
+            else pass = polygons_intersect<KT, KS>(a, na, b, nb);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        int pos = 0;
+        if (m) {
+            if (lane == __ffs(m) - 1) pos = atomicAdd(&s_cnt, __popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        if (tid == 0 && s_cnt > 0) s_base = atomicAdd(ctr + CTR_SURV, (unsigned long long)s_cnt);
+        __syncthreads();
+        if (pass) surv[s_base + pos] = pr;
     }
 }
 
-template <int KT, int KS>
-__global__ void __launch_bounds__(CLIP_T, 3)
-k_clip_survivors(const Survivor *__restrict__ surv, const unsigned long long *__restrict__ n_surv,
+template <int KT, int KS, int BT, int MINB>
+__global__ void __launch_bounds__(BT, MINB)
+k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__restrict__ ctr,
                  const double2 *__restrict__ tpoly, const uint8_t *__restrict__ tnv, int kt,
                  const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks,
-                 double *__restrict__ area) {
+                 const int32_t *__restrict__ tperm, int64_t t_begin, double *__restrict__ area,
+                 int32_t *__restrict__ row_cnt) {
     extern __shared__ double2 s_buf[];
-    const int64_t q = blockIdx.x * (int64_t)CLIP_T + threadIdx.x;
-    if (q >= (int64_t)*n_surv) return;
-    const Survivor r = surv[q];
+    const unsigned long long n_surv = ctr[CTR_SURV];
     double2 *bufA = s_buf + threadIdx.x;
-    double2 *bufB = s_buf + (size_t)(KT + KS) * CLIP_T + threadIdx.x;
-    double2 a[KT], b[KS];
-    const int na = load_poly<KT>(tpoly, tnv, r.tgt, kt, a);
-    const int nb = load_poly<KS>(spoly, snv, r.src, ks, b);
-    bool fb = false;
-    double ar = clip_area_dense<KT, KS>(a, na, b, nb, bufA, bufB, CLIP_T, &fb);
-    if (fb) ar = clip_area_fallback<KT, KS>(a, na, b, nb, bufA, bufB, CLIP_T);
-    area[r.pair] = ar;
+    double2 *bufB = s_buf + (size_t)(KT + KS) * BT + threadIdx.x;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * BT + threadIdx.x; q < n_surv;
+         q += (unsigned long long)gridDim.x * BT) {
+        const int2 r = surv[q];
+        double2 a[KT], b[KS];
+        const int na = load_poly<KT>(tpoly, tnv, r.x, kt, a);
+        const int nb = load_poly<KS>(spoly, snv, r.y, ks, b);
+        double ar;
+        if (KT + KS <= 32) {
+            bool fb = false;
+            ar = clip_area_dense<KT, KS>(a, na, b, nb, bufA, bufB, BT, &fb);
+            if (fb) ar = clip_area_fallback<KT, KS>(a, na, b, nb, bufA, bufB, BT);
+        } else {
+            ar = clip_area<KT, KS>(a, na, b, nb, bufA, bufB, BT);
+        }
+        if (!(ar > 0.0)) ar = 0.0;
+        area[q] = ar;
+        if (ar > 0.0) atomicAdd(row_cnt + (tperm[r.x] - t_begin), 1);
+    }
 }
 
-template <int KT, int KS>
-static int launch_clip_dense(const int32_t *ct, const int32_t *cs, int64_t n_pairs,
-                             const double *tpoly, const uint8_t *tnv, int kt, const double *spoly,
-                             const uint8_t *snv, int ks, double *area, void *surv,
-                             unsigned long long *stats, cudaStream_t s) {
-    const unsigned grid = (unsigned)div_up(n_pairs, CLIP_T);
-    k_sat<KT, KS><<<grid, CLIP_T, 0, s>>>(ct, cs, n_pairs, (const double2 *)tpoly, tnv, kt,
-                                          (const double2 *)spoly, snv, ks, area, (Survivor *)surv, stats);
-    XG_CHECK_LAUNCH();
-    const size_t smem = sizeof(double2) * 2 * (size_t)(KT + KS) * CLIP_T;
-    XG_CUDA(cudaFuncSetAttribute(k_clip_survivors<KT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_clip_survivors<KT, KS><<<grid, CLIP_T, smem, s>>>((const Survivor *)surv, stats + 3, (const double2 *)tpoly, tnv, kt,
-                                                        (const double2 *)spoly, snv, ks, area);
-    XG_CHECK_LAUNCH();
-    return XG_OK;
+// area of a packed face with the reference's arithmetic (connectivity.py:615-633:
+// shoelace relative to the first vertex of the ORIGINAL vertex order)
+__device__ __forceinline__ double packed_face_area(const double2 *__restrict__ poly, uint8_t nvf) {
+    const int n = nvf & 0x7f;
+    const bool flip = nvf & 0x80;
+    const double2 v0 = poly[flip ? n - 1 : 0];
+    double det = 0.0;
+    for (int j = 0; j < n; ++j) {
+        const int ja = flip ? n - 1 - j : j;
+        const int jn = (j + 1 < n) ? j + 1 : 0;
+        const int jb = flip ? n - 1 - jn : jn;
+        const double ax = poly[ja].x - v0.x, ay = poly[ja].y - v0.y;
+        const double bx = poly[jb].x - v0.x, by = poly[jb].y - v0.y;
+        det += ax * by - ay * bx;
+    }
+    return 0.5 * fabs(det);
+}
+
+// one thread per survivor: a positive area takes the next free slot of its row
+// (row_cnt counts down, so the row fills from the back; k_sort_rows orders it)
+__global__ void __launch_bounds__(256)
+k_scatter(const int2 *__restrict__ surv, const double *__restrict__ area, unsigned long long n_surv,
+          const int32_t *__restrict__ tperm, int64_t t_begin, const int32_t *__restrict__ sperm,
+          const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks, int relative,
+          const int64_t *__restrict__ indptr, int32_t *__restrict__ row_cnt,
+          int32_t *__restrict__ indices, double *__restrict__ data) {
+    for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n_surv;
+         q += (unsigned long long)gridDim.x * blockDim.x) {
+        double a = area[q];
+        if (!(a > 0.0)) continue;
+        const int2 r = surv[q];
+        const int64_t row = tperm[r.x] - t_begin;
+        const int slot = atomicSub(row_cnt + row, 1) - 1;
+        const int64_t pos = indptr[row] + slot;
+        if (relative) a = a / packed_face_area(spoly + (int64_t)r.y * ks, snv[r.y]);
+        indices[pos] = sperm[r.y];
+        data[pos] = a;
+    }
+}
+
+__device__ __forceinline__ void cswap(int32_t &ka, double &va, int32_t &kb, double &vb) {
+    const bool sw = ka > kb;
+    const int32_t tk = sw ? kb : ka;
+    const double tv = sw ? vb : va;
+    kb = sw ? ka : kb;
+    vb = sw ? va : vb;
+    ka = tk;
+    va = tv;
+}
+
+// one thread per row: ascending source index.  Rows of up to 8 entries (the
+// common case) are sorted in registers with a fixed network; longer rows fall
+// back to an in-place insertion sort.
+__global__ void __launch_bounds__(256)
+k_sort_rows(const int64_t *__restrict__ indptr, int64_t n_rows, int32_t *__restrict__ indices,
+            double *__restrict__ data) {
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const int64_t b = indptr[row];
+    const int n = (int)(indptr[row + 1] - b);
+    if (n < 2) return;
+    if (n <= 8) {
+        int32_t k[8];
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            k[i] = i < n ? indices[b + i] : 0x7fffffff;
+            v[i] = i < n ? data[b + i] : 0.0;
+        }
+        // 19-comparator network for 8 keys
+#define XG_CS(i, j) cswap(k[i], v[i], k[j], v[j])
+        XG_CS(0, 1); XG_CS(2, 3); XG_CS(4, 5); XG_CS(6, 7);
+        XG_CS(0, 2); XG_CS(1, 3); XG_CS(4, 6); XG_CS(5, 7);
+        XG_CS(1, 2); XG_CS(5, 6); XG_CS(0, 4); XG_CS(3, 7);
+        XG_CS(1, 5); XG_CS(2, 6);
+        XG_CS(1, 4); XG_CS(3, 6);
+        XG_CS(2, 4); XG_CS(3, 5);
+        XG_CS(3, 4);
+#undef XG_CS
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < n) {
+                indices[b + i] = k[i];
+                data[b + i] = v[i];
+            }
+        return;
+    }
+    for (int i = 1; i < n; ++i) {
+        const int32_t key = indices[b + i];
+        const double val = data[b + i];
+        int j = i - 1;
+        while (j >= 0 && indices[b + j] > key) {
+            indices[b + j + 1] = indices[b + j];
+            data[b + j + 1] = data[b + j];
+            --j;
+        }
+        indices[b + j + 1] = key;
+        data[b + j + 1] = val;
+    }
 }
 
 struct CastI64 {
     __host__ __device__ __forceinline__ int64_t operator()(const int32_t &v) const { return (int64_t)v; }
 };
 
-template <int KT, int KS>
-static int launch_clip(int block, const int32_t *ct, const int32_t *cs, int64_t n_pairs,
-                       const double *tpoly, const uint8_t *tnv, int kt, const double *spoly,
-                       const uint8_t *snv, int ks, double *area, unsigned long long *stats,
-                       cudaStream_t s) {
-    const size_t smem = sizeof(double2) * 2 * (size_t)(KT + KS) * block;
-    if (smem > 48 * 1024)
-        XG_CUDA(cudaFuncSetAttribute(k_clip<KT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_clip<KT, KS><<<(unsigned)div_up(n_pairs, block), block, smem, s>>>(
-        ct, cs, n_pairs, (const double2 *)tpoly, tnv, kt, (const double2 *)spoly, snv, ks, area, stats);
+struct ClipArgs {
+    const int2 *pairs;
+    unsigned long long cap;
+    const double *tpoly;
+    const uint8_t *tnv;
+    int kt;
+    const double *spoly;
+    const uint8_t *snv;
+    int ks;
+    int2 *surv;
+    unsigned long long *ctr;
+    const int32_t *tperm;
+    int64_t t_begin;
+    double *area;
+    int32_t *row_cnt;
+    cudaEvent_t between;  // recorded between the two kernels (phase timing)
+};
+
+template <int KT, int KS, int BT, int MINB>
+static int launch_clip(const ClipArgs &A, cudaStream_t s) {
+    int per_sm = 1;
+    XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sat<KT, KS, BT>, BT, 0));
+    if (per_sm < 1) per_sm = 1;
+    k_sat<KT, KS, BT><<<NUM_SMS * per_sm, BT, 0, s>>>(A.pairs, A.cap, (const double2 *)A.tpoly, A.tnv, A.kt,
+                                                     (const double2 *)A.spoly, A.snv, A.ks, A.surv, A.ctr);
+    XG_CHECK_LAUNCH();
+    if (A.between) XG_CUDA(cudaEventRecord(A.between, s));
+    const size_t smem = sizeof(double2) * 2 * (size_t)(KT + KS) * BT;
+    auto kern = k_clip_survivors<KT, KS, BT, MINB>;
+    XG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem));
+    if (per_sm < 1) per_sm = 1;
+    kern<<<NUM_SMS * per_sm, BT, smem, s>>>(A.surv, A.ctr, (const double2 *)A.tpoly, A.tnv, A.kt,
+                                            (const double2 *)A.spoly, A.snv, A.ks, A.tperm, A.t_begin,
+                                            A.area, A.row_cnt);
     XG_CHECK_LAUNCH();
     return XG_OK;
 }
@@ -369,21 +395,23 @@ struct xg_overlap {
     const xg_index *src = nullptr;
     int64_t t_begin = 0, n_t = 0;
     int k_t = 0;
-    int64_t n_cand = 0, nnz = 0;
+    int64_t n_cand = 0, n_surv = 0, nnz = 0;
     cudaStream_t s = nullptr;
     // device buffers
-    DevBuf tperm, tbox, tpoly, tnv, cand_ptr, cand_src, cand_tgt, area, stats;
+    DevBuf tperm, tbox, tpoly, tnv, pairs, surv, area, row_cnt, ctr;
     int64_t h_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool stats_valid = false;
-    // phase timing: ev[i] is recorded when phase i starts, ev[n_ev-1] at the end
+    // phase timing: ev[i] is recorded when phase i starts, the last one at the end
     cudaEvent_t ev[XG_N_PHASES + 1];
     int n_ev = 0;
     double h_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     xg_overlap() { for (int i = 0; i <= XG_N_PHASES; ++i) ev[i] = nullptr; }
     ~xg_overlap() { for (int i = 0; i <= XG_N_PHASES; ++i) if (ev[i]) cudaEventDestroy(ev[i]); }
     cudaError_t mark() {
-        cudaError_t e = cudaEventCreate(&ev[n_ev]);
-        if (e != cudaSuccess) return e;
+        if (!ev[n_ev]) {
+            cudaError_t e = cudaEventCreate(&ev[n_ev]);
+            if (e != cudaSuccess) return e;
+        }
         return cudaEventRecord(ev[n_ev++], s);
     }
     void collect() {
@@ -393,6 +421,82 @@ struct xg_overlap {
         }
     }
 };
+
+// one attempt with a pair arena of `cap` entries; *needed receives the number of
+// candidate pairs the walk found (> cap means: run again with that capacity)
+static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_indptr,
+                           unsigned long long *needed) {
+    const xg_index *source = job->src;
+    cudaStream_t s = job->s;
+    const int64_t n_t = job->n_t;
+    const int k_t = job->k_t, ks = source->k;
+    job->n_ev = 1;  // keep ev[0] (pack start), re-record the rest
+
+    XG_CUDA(cudaMemsetAsync(job->ctr.p, 0, sizeof(unsigned long long) * CTR_N, s));
+    XG_CUDA(job->pairs.alloc(sizeof(int2) * (size_t)cap, s));
+    XG_CUDA(job->surv.alloc(sizeof(int2) * (size_t)cap, s));
+    XG_CUDA(job->area.alloc(sizeof(double) * (size_t)cap, s));
+    XG_CUDA(cudaMemsetAsync(job->row_cnt.p, 0, sizeof(int32_t) * (size_t)(n_t + 1), s));
+
+    TraverseParams P;
+    P.boxes[0] = source->leaf_box; P.count[0] = source->n_face;
+    for (int l = 0; l < source->n_levels; ++l) { P.boxes[l + 1] = source->level_box[l]; P.count[l + 1] = source->level_n[l]; }
+    P.top = source->n_levels + 1;
+    const unsigned tiles = (unsigned)div_up(n_t, 32);
+    XG_CUDA(job->mark());  // XG_PHASE_TRAVERSE
+    k_traverse<<<(unsigned)div_up(tiles, TRAV_WARPS), TRAV_WARPS * 32, 0, s>>>(
+        P, job->tbox.as<Box>(), n_t, job->pairs.as<int2>(), cap, job->ctr.as<unsigned long long>());
+    XG_CHECK_LAUNCH();
+
+    XG_CUDA(job->mark());  // XG_PHASE_SAT
+    ClipArgs A;
+    A.pairs = job->pairs.as<int2>(); A.cap = cap;
+    A.tpoly = job->tpoly.as<double>(); A.tnv = job->tnv.as<uint8_t>(); A.kt = k_t;
+    A.spoly = source->poly; A.snv = source->nvert; A.ks = ks;
+    A.surv = job->surv.as<int2>(); A.ctr = job->ctr.as<unsigned long long>();
+    A.tperm = job->tperm.as<int32_t>(); A.t_begin = job->t_begin;
+    A.area = job->area.as<double>(); A.row_cnt = job->row_cnt.as<int32_t>();
+    if (!job->ev[job->n_ev]) XG_CUDA(cudaEventCreate(&job->ev[job->n_ev]));
+    A.between = job->ev[job->n_ev++];  // XG_PHASE_CLIP starts between the two kernels
+    int rc;
+    if (k_t == 3 && ks == 3) rc = launch_clip<3, 3, 256, 3>(A, s);
+    else if (k_t == 3 && ks == 4) rc = launch_clip<3, 4, 256, 3>(A, s);
+    else if (k_t == 4 && ks == 3) rc = launch_clip<4, 3, 256, 3>(A, s);
+    else if (k_t == 4 && ks == 4) rc = launch_clip<4, 4, 256, 3>(A, s);
+    else if (k_t <= 8 && ks <= 8) rc = launch_clip<8, 8, 128, 2>(A, s);
+    else if (k_t <= 16 && ks <= 16) rc = launch_clip<16, 16, 64, 1>(A, s);
+    else rc = launch_clip<XG_MAX_N_VERTEX, XG_MAX_N_VERTEX, 32, 1>(A, s);
+    if (rc) return rc;
+
+    XG_CUDA(job->mark());  // XG_PHASE_ROWPTR
+    {
+        cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(job->row_cnt.as<int32_t>(), CastI64());
+        size_t tb = 0;
+        XG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, d_indptr, n_t + 1, s));
+        DevBuf tmp;
+        XG_CUDA(tmp.alloc(tb, s));
+        XG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, d_indptr, n_t + 1, s));
+    }
+    int64_t nnz = 0;
+    unsigned long long hc[CTR_N];
+    XG_CUDA(cudaMemcpyAsync(&nnz, d_indptr + n_t, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    XG_CUDA(cudaMemcpyAsync(hc, job->ctr.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    XG_CUDA(job->mark());  // end
+    XG_CUDA(cudaStreamSynchronize(s));
+    *needed = hc[CTR_PAIRS];
+    if (hc[CTR_PAIRS] > cap) return XG_OK;  // caller re-runs
+    job->collect();
+    job->nnz = nnz;
+    job->n_cand = (int64_t)hc[CTR_PAIRS];
+    job->n_surv = (int64_t)hc[CTR_SURV];
+    job->h_stats[0] = n_t;
+    job->h_stats[1] = (int64_t)hc[CTR_VISITS];
+    job->h_stats[2] = (int64_t)hc[CTR_TESTS];
+    job->h_stats[3] = (int64_t)hc[CTR_SURV];
+    job->h_stats[4] = nnz;
+    job->h_stats[5] = (int64_t)hc[CTR_PAIRS];
+    return XG_OK;
+}
 
 extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, int64_t n_t_node,
                                 const void *d_t_faces, int idx_bytes, int64_t n_t_face, int k_t,
@@ -414,115 +518,40 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
     int rc = XG_OK;
 #define OV_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = cuda_fail(e__, #call, __FILE__, __LINE__); goto fail; } } while (0)
     {
-        OV_CUDA(job->stats.alloc(sizeof(unsigned long long) * 8, s));
-        OV_CUDA(cudaMemsetAsync(job->stats.p, 0, sizeof(unsigned long long) * 8, s));
         if (n_t == 0 || source->n_face == 0) {
             OV_CUDA(cudaMemsetAsync(d_indptr, 0, sizeof(int64_t) * (size_t)(n_t + 1), s));
             OV_CUDA(cudaStreamSynchronize(s));
             *h_nnz = 0;
+            job->h_stats[0] = n_t;
             job->stats_valid = true;
             *job_out = job;
             return XG_OK;
         }
         OV_CUDA(job->mark());  // XG_PHASE_PACK
+        OV_CUDA(job->ctr.alloc(sizeof(unsigned long long) * CTR_N, s));
         OV_CUDA(job->tperm.alloc(sizeof(int32_t) * (size_t)n_t, s));
         OV_CUDA(job->tbox.alloc(sizeof(Box) * (size_t)n_t, s));
         OV_CUDA(job->tpoly.alloc(sizeof(double) * 2 * (size_t)k_t * (size_t)n_t, s));
         OV_CUDA(job->tnv.alloc((size_t)n_t, s));
+        OV_CUDA(job->row_cnt.alloc(sizeof(int32_t) * (size_t)(n_t + 1), s));
         PackedMesh pm;
         pm.perm = job->tperm.as<int32_t>(); pm.box = job->tbox.as<Box>();
         pm.poly = job->tpoly.as<double>(); pm.nvert = job->tnv.as<uint8_t>();
         rc = pack_mesh(d_t_xy, d_t_faces, idx_bytes, t_begin, t_end, k_t, source->d_frame, nullptr, &pm, s);
         if (rc) goto fail;
 
-        TraverseParams P;
-        P.boxes[0] = source->leaf_box; P.count[0] = source->n_face;
-        for (int l = 0; l < source->n_levels; ++l) { P.boxes[l + 1] = source->level_box[l]; P.count[l + 1] = source->level_n[l]; }
-        P.top = source->n_levels + 1;
-        const unsigned tiles = (unsigned)div_up(n_t, 32);
-        const unsigned tblocks = (unsigned)div_up(tiles, TRAV_WARPS);
-
-        // count pass
-        OV_CUDA(job->mark());  // XG_PHASE_COUNT
-        DevBuf cnt;
-        OV_CUDA(cnt.alloc(sizeof(int32_t) * (size_t)(n_t + 1), s));
-        OV_CUDA(cudaMemsetAsync(cnt.as<int32_t>() + n_t, 0, sizeof(int32_t), s));
-        k_traverse<false><<<tblocks, TRAV_WARPS * 32, 0, s>>>(P, job->tbox.as<Box>(), n_t, cnt.as<int32_t>(), nullptr,
-                                                             nullptr, nullptr, job->stats.as<unsigned long long>());
-        OV_CUDA(cudaGetLastError());
-        OV_CUDA(job->mark());  // XG_PHASE_SCAN
-        OV_CUDA(job->cand_ptr.alloc(sizeof(int64_t) * (size_t)(n_t + 1), s));
-        {
-            cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(cnt.as<int32_t>(), CastI64());
-            size_t tb = 0;
-            OV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, job->cand_ptr.as<int64_t>(), n_t + 1, s));
-            DevBuf tmp;
-            OV_CUDA(tmp.alloc(tb, s));
-            OV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, job->cand_ptr.as<int64_t>(), n_t + 1, s));
-        }
-        int64_t n_cand = 0;
-        OV_CUDA(cudaMemcpyAsync(&n_cand, job->cand_ptr.as<int64_t>() + n_t, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        OV_CUDA(cudaStreamSynchronize(s));
-        job->n_cand = n_cand;
-
-        // fill pass
-        OV_CUDA(job->mark());  // XG_PHASE_FILL
-        OV_CUDA(job->cand_src.alloc(sizeof(int32_t) * (size_t)n_cand, s));
-        OV_CUDA(job->cand_tgt.alloc(sizeof(int32_t) * (size_t)n_cand, s));
-        OV_CUDA(job->area.alloc(sizeof(double) * (size_t)n_cand, s));
-        k_traverse<true><<<tblocks, TRAV_WARPS * 32, 0, s>>>(P, job->tbox.as<Box>(), n_t, nullptr, job->cand_ptr.as<int64_t>(),
-                                                            job->cand_src.as<int32_t>(), job->cand_tgt.as<int32_t>(), nullptr);
-        OV_CUDA(cudaGetLastError());
-
-        // clip
-        OV_CUDA(job->mark());  // XG_PHASE_CLIP
-        if (n_cand > 0) {
-            const int ks = source->k;
-            const int32_t *ct = job->cand_tgt.as<int32_t>(), *cs = job->cand_src.as<int32_t>();
-            const double *tp = job->tpoly.as<double>();
-            const uint8_t *tnv = job->tnv.as<uint8_t>();
-            unsigned long long *st = job->stats.as<unsigned long long>();
-            double *ar = job->area.as<double>();
-            DevBuf surv;  // compact list of pairs that pass the separating-axis filter
-            if (k_t <= 8 && ks <= 8) OV_CUDA(surv.alloc(sizeof(Survivor) * (size_t)n_cand, s));
-            if (k_t == 3 && ks == 3) rc = launch_clip_dense<3, 3>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, surv.p, st, s);
-            else if (k_t == 3 && ks == 4) rc = launch_clip_dense<3, 4>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, surv.p, st, s);
-            else if (k_t == 4 && ks == 3) rc = launch_clip_dense<4, 3>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, surv.p, st, s);
-            else if (k_t == 4 && ks == 4) rc = launch_clip_dense<4, 4>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, surv.p, st, s);
-            else if (k_t <= 8 && ks <= 8) rc = launch_clip_dense<8, 8>(ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, surv.p, st, s);
-            else rc = launch_clip<XG_MAX_N_VERTEX, XG_MAX_N_VERTEX>(32, ct, cs, n_cand, tp, tnv, k_t, source->poly, source->nvert, ks, ar, st, s);
+        unsigned long long cap = (unsigned long long)n_t * PAIRS_PER_TARGET_GUESS;
+        if (cap < 65536) cap = 65536;
+        unsigned long long needed = 0;
+        rc = overlap_attempt(job, cap, d_indptr, &needed);
+        if (rc) goto fail;
+        if (needed > cap) {
+            // denser than guessed: the first walk counted exactly what is needed
+            rc = overlap_attempt(job, needed, d_indptr, &needed);
             if (rc) goto fail;
         }
-
-        // CSR row pointer in the caller's row order (cnt is reused as row counts)
-        OV_CUDA(job->mark());  // XG_PHASE_ROWPTR
-        k_row_count<<<(unsigned)div_up(n_t, 256), 256, 0, s>>>(job->cand_ptr.as<int64_t>(), job->area.as<double>(),
-                                                              job->tperm.as<int32_t>(), t_begin, n_t, cnt.as<int32_t>());
-        OV_CUDA(cudaGetLastError());
-        {
-            cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(cnt.as<int32_t>(), CastI64());
-            size_t tb = 0;
-            OV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, d_indptr, n_t + 1, s));
-            DevBuf tmp;
-            OV_CUDA(tmp.alloc(tb, s));
-            OV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, d_indptr, n_t + 1, s));
-        }
-        int64_t nnz = 0;
-        unsigned long long hs[8];
-        OV_CUDA(cudaMemcpyAsync(&nnz, d_indptr + n_t, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        OV_CUDA(cudaMemcpyAsync(hs, job->stats.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
-        OV_CUDA(job->mark());  // end
-        OV_CUDA(cudaStreamSynchronize(s));
-        job->collect();
-        job->nnz = nnz;
-        job->h_stats[0] = n_t;
-        job->h_stats[1] = (int64_t)hs[0] * 2;  // the walk runs twice (count + fill)
-        job->h_stats[2] = (int64_t)hs[1] * 2;
-        job->h_stats[3] = (int64_t)hs[3];
-        job->h_stats[4] = nnz;
-        job->h_stats[5] = n_cand;
         job->stats_valid = true;
-        *h_nnz = nnz;
+        *h_nnz = job->nnz;
         *job_out = job;
         return XG_OK;
     }
@@ -540,12 +569,13 @@ extern "C" int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32
     if (job->nnz > 0) {
         if (!d_indices || !d_area || !d_indptr) { set_error("xg_overlap_finish: NULL output"); delete job; return XG_ERR_INVALID; }
         const xg_index *src = job->src;
-        k_emit<<<(unsigned)div_up(job->n_t, 256), 256, 0, s>>>(
-            job->cand_ptr.as<int64_t>(), job->cand_src.as<int32_t>(), job->area.as<double>(),
-            job->tperm.as<int32_t>(), job->t_begin, job->n_t, src->perm, (const double2 *)src->poly,
-            src->nvert, src->k, relative, d_indptr, d_indices, d_area);
+        k_scatter<<<NUM_SMS * 8, 256, 0, s>>>(
+            job->surv.as<int2>(), job->area.as<double>(), (unsigned long long)job->n_surv,
+            job->tperm.as<int32_t>(), job->t_begin, src->perm, (const double2 *)src->poly, src->nvert,
+            src->k, relative, d_indptr, job->row_cnt.as<int32_t>(), d_indices, d_area);
+        k_sort_rows<<<(unsigned)div_up(job->n_t, 256), 256, 0, s>>>(d_indptr, job->n_t, d_indices, d_area);
         cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) rc = cuda_fail(e, "k_emit", __FILE__, __LINE__);
+        if (e != cudaSuccess) rc = cuda_fail(e, "k_scatter/k_sort_rows", __FILE__, __LINE__);
     }
     // buffers are released stream-ordered on the stream that produced them
     if (s != job->s) cudaStreamSynchronize(s);
