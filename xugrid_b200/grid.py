@@ -64,6 +64,9 @@ class Ugrid2d:
         self._faces_d = None
         self._centroids = None
         self._area = None
+        self._xy_pin = None
+        self._faces_pin = None
+        self._ready = None
 
     # ---- basic properties -------------------------------------------------------
     @property
@@ -101,14 +104,43 @@ class Ugrid2d:
             return torch.device("cuda", torch.cuda.current_device())
         return torch.device(self.device)
 
+    def prefetch(self) -> None:
+        """Start the host-to-device copy of the mesh on the side (copy) stream.
+        The first call pins a host staging copy; later uploads (after
+        ``release_device``) are asynchronous DMA transfers that overlap with
+        kernels on the compute stream."""
+        if self._xy_d is not None:
+            return
+        _native.lib()  # raises when there is no GPU: no CPU fallback
+        dev = self._dev()
+        if self._xy_pin is None:
+            self._xy_pin = torch.from_numpy(self.node_coordinates).pin_memory()
+            self._faces_pin = torch.from_numpy(self.face_node_connectivity).pin_memory()
+        copy_stream = _copy_stream(dev)
+        with torch.cuda.stream(copy_stream):
+            self._xy_d = self._xy_pin.to(dev, non_blocking=True)
+            self._faces_d = self._faces_pin.to(dev, non_blocking=True)
+            self._ready = torch.cuda.Event()
+            self._ready.record(copy_stream)
+
     def device_arrays(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """(n_node, 2) float64 and (n_face, k) int tensors in HBM (cached)."""
-        if self._xy_d is None:
-            _native.lib()  # raises when there is no GPU: no CPU fallback
-            dev = self._dev()
-            self._xy_d = to_device(self.node_coordinates, torch.float64, dev)
-            self._faces_d = faces_to_device(self.face_node_connectivity, FILL_VALUE, dev)
+        self.prefetch()
+        if self._ready is not None:
+            cur = torch.cuda.current_stream(self._xy_d.device)
+            cur.wait_event(self._ready)
+            self._xy_d.record_stream(cur)
+            self._faces_d.record_stream(cur)
+            self._ready = None
         return self._xy_d, self._faces_d
+
+    def release_device(self) -> None:
+        """Drop the device mirrors and the spatial index (the pinned host
+        staging copy is kept); the next use uploads again."""
+        self._celltree = None
+        self._xy_d = None
+        self._faces_d = None
+        self._ready = None
 
     @property
     def celltree(self) -> CellTree2d:
@@ -199,6 +231,16 @@ class Ugrid2d:
         y = bounds1d_to_vertices(y_bounds)
         node_y, node_x = (a.ravel() for a in np.meshgrid(y, x, indexing="ij"))
         return Ugrid2d._from_intervals_helper(node_x, node_y, nx, ny, name)
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev: torch.device) -> "torch.cuda.Stream":
+    key = (dev.type, dev.index)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
 
 
 def _host(a):

@@ -204,6 +204,10 @@ class BaseRegridder(abc.ABC):
         self._target = setup_grid(target)
         self._weights = None
         self._target_range = target_range
+        # start both uploads on the copy stream: the index build over the source
+        # overlaps with the transfer of the target
+        for side in (self._source, self._target):
+            side.to_unstructured().ugrid_topology.prefetch()
         self._compute_weights(self._source, self._target, tolerance)
 
     # ---- method selection (regridder.py:124-141) --------------------------------------
@@ -253,8 +257,9 @@ class BaseRegridder(abc.ABC):
         first_dims_shape = tuple(source.shape[: source.ndim - nd])
         is_tensor = isinstance(source, torch.Tensor)
         dev = self._weights.data.device
+        host_tensor = is_tensor and not source.is_cuda
         if is_tensor:
-            src = source.reshape((-1, source_grid.size)).to(dev, torch.float64).contiguous()
+            src = source.reshape((-1, source_grid.size)).to(dev, non_blocking=True).to(torch.float64).contiguous()
         else:
             a = np.ascontiguousarray(np.asarray(source).reshape((-1, source_grid.size)))
             src = torch.from_numpy(a).to(dev, non_blocking=True).to(torch.float64)
@@ -264,6 +269,12 @@ class BaseRegridder(abc.ABC):
         else:
             out_shape = first_dims_shape + (self._rows(),)
         out = out.reshape(out_shape)
+        if host_tensor:
+            # host tensor in -> host tensor out (pinned if the input was): async D2H + one sync
+            res = torch.empty(out_shape, dtype=torch.float64, pin_memory=source.is_pinned())
+            res.copy_(out, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return res
         return out if is_tensor else out.cpu().numpy()
 
     def regrid(self, data):
