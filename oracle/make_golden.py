@@ -127,12 +127,59 @@ def golden_connectivity(ns):
     )
 
 
+def golden_barycentric(ns):
+    """Reference pipeline of UnstructuredGrid2d.barycentric (unstructured.py:146-201) with the
+    reference's own voronoi.py / connectivity.py / replace_interpolated_weights; the two
+    numba_celltree calls in it (compute_barycentric_weights, locate_points) go through the oracle."""
+    import oracle
+    from xugrid_b200 import synthetic
+
+    cases = {}
+    dxy, df = synthetic.disk()
+    gx = np.arange(-10.0, 10.0, 0.5) + 0.25
+    yy, xx = np.meshgrid(gx, gx, indexing="ij")
+    cases["disk"] = (dxy, df, np.column_stack([xx.ravel(), yy.ravel()]))
+    mxy, mf = mixed_mesh(seed=8, nx=12, ny=10)
+    rng = np.random.default_rng(4)
+    cases["mixed"] = (mxy, mf, np.column_stack([rng.uniform(-0.5, 12.5, 3000), rng.uniform(-0.5, 10.5, 3000)]))
+    out = {}
+    for name, (xy, faces, points) in cases.items():
+        conn = ns.connectivity
+        node_face = conn.invert_dense_to_sparse(faces)
+        edge_node, face_edge = conn.edge_connectivity(faces)
+        edge_face = conn.invert_dense(face_edge)
+        centroids = conn.centroids(faces, xy[:, 0], xy[:, 1])
+        vertices, vfaces, node_to_face_index, node_to_node_map = ns.voronoi.voronoi_topology(
+            node_face, xy, centroids, edge_face_connectivity=edge_face, edge_node_connectivity=edge_node,
+            add_exterior=True, add_vertices=True, skip_concave=True)
+        vfaces = np.ascontiguousarray(vfaces, dtype=np.int64)
+        tree = oracle.CellTree2d(vertices, vfaces, -1)
+        face_index, weights = tree.compute_barycentric_weights(points)
+        ns.replace_interpolated_weights(vertices, vfaces, face_index, weights, node_to_node_map,
+                                        len(vertices) - len(node_to_node_map))
+        outside = oracle.CellTree2d(xy, faces, -1).locate_points(points) == -1
+        weights[outside] = 0
+        keep = weights.ravel() > 0
+        source_index = node_to_face_index[vfaces[face_index]].ravel()[keep]
+        n_points, n_max = weights.shape
+        target_index = np.repeat(np.arange(n_points), n_max)[keep]
+        w = weights.ravel()[keep]
+        order = np.lexsort((w, source_index, target_index))
+        out[f"{name}_xy"], out[f"{name}_faces"], out[f"{name}_points"] = xy, faces, points
+        out[f"{name}_target"], out[f"{name}_source"], out[f"{name}_weight"] = target_index[order], source_index[order], w[order]
+        out[f"{name}_vor_n_vertex"] = len(vertices)
+        out[f"{name}_vor_area"] = np.sort(conn.area(vfaces, vertices[:, 0], vertices[:, 1]))
+        print("barycentric", name, len(w), "triplets", vfaces.shape)
+    np.savez_compressed(os.path.join(OUT, "barycentric_golden.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
     golden_apply(ns)
     golden_coo(ns)
     golden_connectivity(ns)
+    golden_barycentric(ns)
     print("golden vectors written to", OUT)
 
 

@@ -376,6 +376,7 @@ typedef struct xo_celltree {
     int k;
     double *xy;        /* (n_node, 2) copy */
     i64 *faces;        /* (n_face, k) copy, CCW enforced */
+    char *flipped;     /* (n_face) 1 where the CCW copy reverses the caller's vertex order */
     double *bb;        /* (n_face, 4) */
     i64 *bb_indices;   /* (n_face) */
     xo_node *nodes;
@@ -550,6 +551,8 @@ xo_celltree *xo_celltree_create(const double *xy, i64 n_node, const i64 *faces, 
     t->faces = (i64 *)malloc(sizeof(i64) * (size_t)(n_face > 0 ? n_face * k : 1));
     memcpy(t->faces, faces, sizeof(i64) * (size_t)(n_face * k));
     xo_counter_clockwise(t->xy, t->faces, n_face, k);
+    t->flipped = (char *)malloc((size_t)(n_face > 0 ? n_face : 1));
+    for (i64 f = 0; f < n_face; ++f) t->flipped[f] = (char)(t->faces[f * k] != faces[f * k]);
     t->bb = (double *)malloc(sizeof(double) * 4 * (size_t)(n_face > 0 ? n_face : 1));
     xo_build_bboxes(t->xy, t->faces, n_face, k, t->bb);
     t->bb_indices = (i64 *)malloc(sizeof(i64) * (size_t)(n_face > 0 ? n_face : 1));
@@ -571,7 +574,7 @@ xo_celltree *xo_celltree_create(const double *xy, i64 n_node, const i64 *faces, 
 void xo_celltree_destroy(xo_celltree *t)
 {
     if (!t) return;
-    free(t->xy); free(t->faces); free(t->bb); free(t->bb_indices); free(t->nodes);
+    free(t->xy); free(t->faces); free(t->flipped); free(t->bb); free(t->bb_indices); free(t->nodes);
     free(t->scratch); free(t->res_i); free(t->res_j); free(t->res_a);
     free(t);
 }
@@ -856,6 +859,15 @@ void xo_barycentric(const xo_celltree *t, const double *pts, i64 n, double tol, 
         int np = copy_vertices(t->xy, t->faces + f * k, k, poly);
         if (k == 3) bary_triangle(poly, p, w);
         else bary_wachspress(poly, np, p, tol, w);
+        /* Weights are reported in the CALLER's vertex order.  The tree works on a
+         * CCW-forced copy of the faces; xugrid indexes the weights with its own,
+         * unmodified connectivity (unstructured.py:191-193), so for a face given
+         * clockwise the order has to be mapped back.  PARITY UNPINNED: whether
+         * numba_celltree does this (or flips the caller's array in place, which
+         * has the same effect) is not observable in the reference's tests, which
+         * only use counter-clockwise faces. */
+        if (t->flipped[f])
+            for (int a = 0, b = np - 1; a < b; ++a, --b) { double tmp = w[a]; w[a] = w[b]; w[b] = tmp; }
     }
 }
 

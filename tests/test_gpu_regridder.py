@@ -202,3 +202,95 @@ def test_torch_tensor_in_tensor_out_and_target_range(xb):
         b, e = shard_range(len(tf), r, 3)
         parts.append(xb.OverlapRegridder(source, target, target_range=(b, e)).regrid(v))
     assert torch.equal(torch.cat(parts, dim=1).nan_to_num(-1.0), full.nan_to_num(-1.0))
+
+
+# ---------------------------------------------------------------------------- barycentric
+@pytest.mark.parametrize("name", ["disk", "mixed"])
+def test_barycentric_weights_match_reference_pipeline(xb, golden_dir, name):
+    """BarycentricInterpolator weights against the golden triplets produced with the
+    reference's voronoi.py + replace_interpolated_weights (oracle/make_golden.py)."""
+    g = np.load(f"{golden_dir}/barycentric_golden.npz")
+    xy, faces, points = g[f"{name}_xy"], g[f"{name}_faces"], g[f"{name}_points"]
+    source = xb.Ugrid2d(xy[:, 0], xy[:, 1], -1, faces)
+    # target mesh whose face centroids are exactly the golden points: tiny triangles
+    d = 1e-3
+    tri = np.array([[-d, -d], [2 * d, -d], [-d, 2 * d]])  # centroid at the origin
+    txy = (points[:, None, :] + tri[None, :, :]).reshape(-1, 2)
+    tf = np.arange(3 * len(points)).reshape(-1, 3)
+    target = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf)
+    assert np.allclose(oracle.face_centroids(txy, tf), points, atol=1e-15)
+    r = xb.BarycentricInterpolator(source, target)
+    data, indices, indptr = r._weights.to_numpy()
+    tgt = np.repeat(np.arange(len(points)), np.diff(indptr))
+    order = np.lexsort((data, indices, tgt))
+    # centroids of the tiny triangles differ from the golden points by rounding (1e-15), and
+    # Wachspress weights near a polygon edge amplify that: the pair set is identical, weights
+    # agree to 1e-6 here (the exact-point comparison at 1e-10 is tests/test_voronoi_cpu.py and
+    # test_barycentric_parity)
+    assert np.array_equal(tgt[order], g[f"{name}_target"])
+    assert np.array_equal(indices[order], g[f"{name}_source"])
+    assert np.allclose(data[order], g[f"{name}_weight"], rtol=1e-6, atol=1e-9)
+
+
+def test_barycentric_interpolator(xb, disk):
+    # test_regridder.py:187-201: 0.25-spaced quads over the disk
+    square = quads(xb, 0.25).to_ugrid2d()
+    regridder = xb.BarycentricInterpolator(source=disk, target=square)
+    result = regridder.regrid(disk).values
+    assert np.isfinite(result).any()
+    assert np.nanmin(result) >= disk.values.min() and np.nanmax(result) <= disk.values.max()
+    layered = xb.UgridDataArray(np.ones(5)[:, None] * disk.values[None, :], disk.grid, ("layer", disk.grid.face_dimension))
+    broadcasted = regridder.regrid(layered)
+    assert broadcasted.dims == ("layer", square.face_dimension) and broadcasted.shape == (5, 6400)
+    # self-interpolation is the identity (test_unstructured.py:53-59)
+    me = xb.BarycentricInterpolator(disk, disk)
+    data, indices, indptr = me._weights.to_numpy()
+    strong = data > 1e-9
+    rows = np.repeat(np.arange(disk.grid.n_face), np.diff(indptr))
+    assert np.array_equal(rows[strong], np.arange(disk.grid.n_face))
+    assert np.array_equal(indices[strong], np.arange(disk.grid.n_face))
+    assert np.allclose(data[strong], 1.0)
+    # round trips like the other regridders
+    again = xb.BarycentricInterpolator.from_weights(regridder.weights, target=square)
+    assert np.array_equal(again.regrid(disk).values, result, equal_nan=True)
+
+
+def test_barycentric_reproduces_linear_fields(xb):
+    sxy, sf = synthetic.jittered_lattice(40, 40, 5, "mixed")
+    txy, tf = synthetic.jittered_lattice(23, 19, 6, "tri", bounds=(0.1, 0.9, 0.1, 0.9))
+    source = xb.Ugrid2d(sxy[:, 0], sxy[:, 1], -1, sf)
+    target = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf)
+    f = lambda p: 2.0 + 3.0 * p[:, 0] - 1.5 * p[:, 1]
+    out = xb.BarycentricInterpolator(source, target).regrid(f(source.centroids))
+    assert np.allclose(out, f(target.centroids), rtol=0, atol=1e-12)
+
+
+def test_barycentric_concave_known_answer(xb):
+    # /root/reference/tests/test_regrid/test_regridder.py:334-369
+    vertices = np.array([[0.0, 0.0], [3.0, 0.0], [1.0, 1.0], [0.0, 2.0], [3.0, 2.0]])
+    faces = np.array([[0, 1, 2], [0, 2, 3], [2, 4, 3]])
+    grid = xb.Ugrid2d(vertices[:, 0], vertices[:, 1], -1, faces)
+    dx = 0.1
+    x = np.arange(0.0, 3.0, dx) + 0.5 * dx
+    y = np.arange(0.0, 2.0, dx) + 0.5 * dx
+    other = xb.StructuredGrid2d(x, y)
+    result = xb.BarycentricInterpolator(source=grid, target=other).regrid(np.array([2.0, 0.5, 2.0]))
+    assert result.shape == (20, 30)
+    assert np.nanmin(result) >= 0.5 and np.nanmax(result) <= 2.0
+    # There should be a large enough "gap" of NaNs on the right side.
+    assert np.isnan(result).sum() == 200
+
+
+def test_barycentric_structured_source_known_answer(xb):
+    # /root/reference/tests/test_regrid/test_regridder.py:371-405 (the reference takes its
+    # separable linear path for a structured source; here the raster is a quad mesh and the
+    # same numbers come out of the Voronoi / Wachspress path)
+    source = xb.StructuredGrid2d(x=np.array([0.5, 1.5]), y=np.array([1.5, 0.5]))
+    data = np.array([[1.0, 2.0], [3.0, 4.0]])
+    c = np.arange(0.0, 2.0, 0.25) + 0.125
+    target = xb.StructuredGrid2d(c, c)
+    out = xb.BarycentricInterpolator(source, target).regrid(data)
+    assert out.shape == (8, 8)
+    assert np.allclose(out[0], [3.0, 3.0, 3.125, 3.375, 3.625, 3.875, 4.0, 4.0])
+    assert np.allclose(out[-1], [1.0, 1.0, 1.125, 1.375, 1.625, 1.875, 2.0, 2.0])
+    assert np.allclose(out[:, 0], [3.0, 3.0, 2.75, 2.25, 1.75, 1.25, 1.0, 1.0])

@@ -8,6 +8,7 @@ libxgregrid.so (C ABI in include/xg_regrid.h); there is no CPU fallback.
 from .grid import StructuredGrid2d, Ugrid2d, UgridDataArray  # noqa: F401
 from .celltree import CellTree2d  # noqa: F401
 from .regridder import (  # noqa: F401
+    BarycentricInterpolator,
     CentroidLocatorRegridder,
     OverlapRegridder,
     RelativeOverlapRegridder,

@@ -125,6 +125,35 @@ class UnstructuredGrid2d:
         weights = torch.ones(source_index.numel(), dtype=torch.float64, device=idx.device)
         return source_index, target_index, weights
 
+    def barycentric(self, other: "UnstructuredGrid2d", tolerance: Optional[float] = None) -> MatrixCSR:
+        """
+        unstructured.py:146-201 on the device: Voronoi polygons around the
+        source nodes, barycentric weights of the target centroids inside them,
+        corner weights redistributed, points outside the source mesh dropped.
+        Returns the CSR (rows = target faces, columns = source faces).
+        """
+        from . import voronoi
+        from .celltree import CellTree2d
+
+        grid = self.ugrid_topology
+        xy, faces = grid.device_arrays()
+        points = other.ugrid_topology.centroids_device
+        topo = voronoi.voronoi_topology(faces, xy, grid.centroids_device)
+        vor_tree = CellTree2d(topo.vertices, topo.faces, -1, device=xy.device)
+        face_index, weights = vor_tree.compute_barycentric_weights_device(points, tolerance)
+        conn = topo.faces[face_index.long().clamp(min=0)]
+        voronoi.redistribute_corner_weights(topo, conn, weights)
+        outside = grid.celltree.locate_points_device(points) == -1
+        weights[outside] = 0
+        keep = weights > 0
+        source_index = topo.vertex_face[conn.clamp(min=0)]
+        counts = keep.sum(dim=1)
+        indptr = torch.zeros(points.shape[0] + 1, dtype=torch.int64, device=xy.device)
+        torch.cumsum(counts, 0, out=indptr[1:])
+        indices = source_index[keep].to(torch.int32)
+        data = weights[keep]
+        return MatrixCSR(data, indices, indptr, other.size, self.size, int(data.numel()))
+
     def to_dataset(self, name: str) -> dict:
         g = self.ugrid_topology
         return {
@@ -420,4 +449,32 @@ class RelativeOverlapRegridder(BaseOverlapRegridder):
                      method: Union[str, Callable] = "first_order_conservative"):
         instance = super().from_weights(weights, target)
         instance._setup_regrid(method)
+        return instance
+
+
+class BarycentricInterpolator(BaseRegridder):
+    """
+    regridder.py:589-659.  Interpolates between the values of the source faces
+    (located at their centroids) with barycentric weights inside the Voronoi
+    polygons around the source nodes.  A structured source is treated as a quad
+    mesh (the reference's separable ``linear_weights`` path is out of scope).
+    """
+
+    _METHODS = ("mean",)
+
+    def __init__(self, source, target, tolerance: Optional[float] = None):
+        super().__init__(source, target, tolerance)
+        # weights of a target face sum to 1: a weighted mean also handles NaNs
+        self._setup_regrid("mean")
+
+    def _compute_weights(self, source, target, tolerance=None):
+        if self._target_range is not None:
+            raise NotImplementedError("target_range is only supported by the overlap regridders")
+        src, tgt = source.to_unstructured(), target.to_unstructured()
+        self._weights = src.barycentric(tgt, tolerance)
+
+    @classmethod
+    def from_weights(cls, weights: dict, target):
+        instance = super().from_weights(weights, target)
+        instance._setup_regrid("mean")
         return instance
