@@ -173,7 +173,7 @@ def run_ours(args) -> int:
 
     import xugrid_b200 as xb
     from xugrid_b200 import sparse
-    from xugrid_b200.distributed import all_gather_columns, shard_range
+    from xugrid_b200.distributed import all_gather_columns, shard_range, target_range_box
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -200,7 +200,8 @@ def run_ours(args) -> int:
     state = {}
 
     def step(src):
-        tree = xb.CellTree2d(src["sxy"], src["sf"], device=dev)
+        box = target_range_box(src["txy"], src["tf"], b, e) if world > 1 else None
+        tree = xb.CellTree2d(src["sxy"], src["sf"], device=dev, clip_box=box)
         indptr, indices, area = tree.intersect_faces_csr(src["txy"], src["tf"], t_begin=b, t_end=e)
         A = sparse.MatrixCSR(area, indices, indptr, e - b, n_s, int(area.numel()))
         local = sparse.csr_apply(0, 0.0, src["values"], A, e - b)

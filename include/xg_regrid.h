@@ -80,8 +80,20 @@ int xg_release_cached_memory(void);
  * not modified. */
 int xg_index_create(const double *d_xy, int64_t n_node, const void *d_faces, int idx_bytes,
                     int64_t n_face, int k, void *stream, xg_index **out);
+/* Same, but only faces whose bounding box strictly intersects
+ * h_clip_box = [xmin, xmax, ymin, ymax] (host pointer) are indexed: a rank that
+ * owns a contiguous range of target faces builds its index over the part of a
+ * replicated source mesh that its targets can touch.  Face ids reported by
+ * queries are still the caller's.  NULL box = xg_index_create. */
+int xg_index_create_clipped(const double *d_xy, int64_t n_node, const void *d_faces, int idx_bytes,
+                            int64_t n_face, int k, const double *h_clip_box, void *stream,
+                            xg_index **out);
+/* h_box = [xmin, xmax, ymin, ymax] of the vertices of faces [f_begin, f_end):
+ * the clip box of a target shard (synchronises the stream). */
+int xg_face_range_bounds(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
+                         int64_t f_end, int k, double h_box[4], void *stream);
 int xg_index_destroy(xg_index *index);
-/* info[0]=n_face info[1]=k info[2]=levels info[3]=device bytes owned
+/* info[0]=indexed faces info[1]=k info[2]=levels info[3]=device bytes owned
  * info[4]=n_node; tol = default tolerance = 1e-12 * max bbox diagonal
  * (xugrid/ugrid/ugridbase.py:1165-1170) */
 int xg_index_info(const xg_index *index, int64_t info[8], double *default_tolerance);

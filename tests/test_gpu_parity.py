@@ -379,3 +379,26 @@ def test_overlap_dense_sources_rerun_path(xb):
     assert np.diff(indptr).max() > 8
     rows = np.repeat(np.arange(len(tf)), np.diff(indptr))
     assert np.array_equal(np.lexsort((indices, rows)), np.arange(len(indices)))
+
+
+def test_clipped_index_equals_full_index_on_a_target_range(xb):
+    from xugrid_b200.distributed import shard_range, target_range_box
+
+    sxy, sf = synthetic.delaunay(4000, 31)
+    txy, tf = synthetic.jittered_lattice(40, 40, 32, "tri", bounds=(0.02, 0.98, 0.02, 0.98))
+    full = xb.CellTree2d(sxy, sf)
+    dxy, dtf = torch.from_numpy(txy).cuda(), torch.from_numpy(tf).cuda()
+    for rank in range(4):
+        b, e = shard_range(len(tf), rank, 4)
+        box = target_range_box(dxy, dtf, b, e)
+        part = xb.CellTree2d(sxy, sf, clip_box=box)
+        assert 0 < part.n_indexed < full.n_indexed
+        ref = [t.cpu().numpy() for t in full.intersect_faces_csr(dxy, dtf, t_begin=b, t_end=e)]
+        got = [t.cpu().numpy() for t in part.intersect_faces_csr(dxy, dtf, t_begin=b, t_end=e)]
+        for x, y in zip(ref, got):
+            assert np.array_equal(x, y)
+    # a box that misses the mesh indexes nothing and finds nothing
+    empty = xb.CellTree2d(sxy, sf, clip_box=(5.0, 6.0, 5.0, 6.0))
+    assert empty.n_indexed == 0
+    ip, ix, ar = empty.intersect_faces_csr(dxy, dtf)
+    assert ix.numel() == 0 and int(ip[-1]) == 0

@@ -82,7 +82,10 @@ class OverlapStats(NamedTuple):
 
 
 class CellTree2d:
-    def __init__(self, vertices: ArrayLike, faces: ArrayLike, fill_value: int = -1, device=None):
+    def __init__(self, vertices: ArrayLike, faces: ArrayLike, fill_value: int = -1, device=None,
+                 clip_box=None):
+        """``clip_box=(xmin, xmax, ymin, ymax)`` indexes only the faces whose bounding
+        box meets the box (used by ranks that own a range of target faces)."""
         L = _native.lib()
         self.device = _device(device)
         with torch.cuda.device(self.device):
@@ -93,10 +96,11 @@ class CellTree2d:
             self.n_face, self.k = int(self.faces.shape[0]), int(self.faces.shape[1])
             self.n_node = int(self.vertices.shape[0])
             h = ctypes.c_void_p()
+            box = None if clip_box is None else (ctypes.c_double * 4)(*[float(v) for v in clip_box])
             _native.check(
-                L.xg_index_create(
+                L.xg_index_create_clipped(
                     _native.ptr(self.vertices), self.n_node, _native.ptr(self.faces),
-                    self.faces.element_size(), self.n_face, self.k, _native.stream_ptr(),
+                    self.faces.element_size(), self.n_face, self.k, box, _native.stream_ptr(),
                     ctypes.byref(h),
                 )
             )
@@ -104,6 +108,7 @@ class CellTree2d:
         info = (ctypes.c_int64 * 8)()
         tol = ctypes.c_double()
         _native.check(L.xg_index_info(self._h, info, ctypes.byref(tol)))
+        self.n_indexed = int(info[0])
         self.n_levels = int(info[2])
         self.device_bytes = int(info[3])
         self.default_tolerance = float(tol.value)

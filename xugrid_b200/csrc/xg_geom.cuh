@@ -254,7 +254,7 @@ __device__ __forceinline__ double clip_area_dense(const double2 (&poly)[KT], int
             int nflip = 0, cj0 = -1, cp0 = 0, cj1 = -1, cp1 = 0;
 #pragma unroll
             for (int j = 0; j < M; ++j) {
-                if (j < length) {
+                if (j < KT + i && j < length) {  // after i clips: at most KT + i vertices
                     const double2 b = sub[j * stride];
                     const bool use = !(b.x == a.x && b.y == a.y);
                     const bool b_in = Ux * (b.y - r.y) > Uy * (b.x - r.x);
@@ -301,7 +301,7 @@ __device__ __forceinline__ double clip_area_dense(const double2 (&poly)[KT], int
             n_out = 0;
 #pragma unroll
             for (int j = 0; j < M; ++j) {
-                if (j < length && ((kept >> j) & 1u)) {
+                if (j < KT + i && j < length && ((kept >> j) & 1u)) {
                     if (j == cj0) { out[n_out * stride] = X0; ++n_out; }
                     else if (j == cj1) { out[n_out * stride] = X1; ++n_out; }
                     if ((inm >> j) & 1u) { out[n_out * stride] = sub[j * stride]; ++n_out; }

@@ -163,13 +163,23 @@ __device__ __forceinline__ uint32_t spread16(uint32_t v) {
     return v;
 }
 
+// optional cull: faces whose bbox does not strictly intersect the box get the
+// key 0xFFFFFFFF (sorted to the end, never packed); kept faces are counted
+struct ClipBox {
+    double xmin, xmax, ymin, ymax;
+    int on;
+};
+
 template <typename I, int KMAX>
 __global__ void __launch_bounds__(256)
 k_face_keys(const double2 *__restrict__ xy, const I *__restrict__ faces, int64_t f_begin,
             int64_t n, int k, const double *__restrict__ frame, uint32_t *__restrict__ keys,
-            int32_t *__restrict__ ids, unsigned long long *diag2_max) {
+            int32_t *__restrict__ ids, unsigned long long *diag2_max, const ClipBox clip,
+            unsigned long long *__restrict__ kept) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     double d2 = 0.0;
+    bool in_box = false;
+    uint32_t my_key = 0;
     if (i < n) {
         const I *face = faces + (f_begin + i) * k;
         double2 p = xy[face[0]];
@@ -188,18 +198,73 @@ k_face_keys(const double2 *__restrict__ xy, const I *__restrict__ faces, int64_t
         const double sx = fx1 > fx0 ? 65536.0 / (fx1 - fx0) : 0.0;
         const double sy = fy1 > fy0 ? 65536.0 / (fy1 - fy0) : 0.0;
         double qx = (cx - fx0) * sx, qy = (cy - fy0) * sy;
-        qx = fmin(fmax(qx, 0.0), 65535.0);
-        qy = fmin(fmax(qy, 0.0), 65535.0);
-        keys[i] = spread16((uint32_t)qx) | (spread16((uint32_t)qy) << 1);
-        ids[i] = (int32_t)(f_begin + i);
+        qx = fmin(fmax(qx, 0.0), 65534.0);  // 0xFFFFFFFF stays free for culled faces
+        qy = fmin(fmax(qy, 0.0), 65534.0);
+        uint32_t key = spread16((uint32_t)qx) | (spread16((uint32_t)qy) << 1);
+        if (clip.on) {
+            in_box = xmin < clip.xmax && clip.xmin < xmax && ymin < clip.ymax && clip.ymin < ymax;
+            if (!in_box) key = 0xFFFFFFFFu;
+        }
+        if (!clip.on) {
+            keys[i] = key;
+            ids[i] = (int32_t)(f_begin + i);
+        }
+        my_key = key;
         const double dx = xmax - xmin, dy = ymax - ymin;
         d2 = dx * dx + dy * dy;
+    }
+    if (clip.on) {
+        // culled build: kept faces are appended compactly (one atomic per warp)
+        const unsigned m = __ballot_sync(0xffffffffu, in_box);
+        if (m) {
+            const int lane = threadIdx.x & 31;
+            unsigned long long base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(kept, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (in_box) {
+                const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+                keys[pos] = my_key;
+                ids[pos] = (int32_t)(f_begin + i);
+            }
+        }
     }
     if (diag2_max) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
         if ((threadIdx.x & 31) == 0 && d2 > 0.0)
             atomicMax(diag2_max, (unsigned long long)__double_as_longlong(d2));
+    }
+}
+
+// red[0..3] = ordered bits of the bounds of the vertices of faces [f_begin, f_begin + n)
+template <typename I>
+__global__ void __launch_bounds__(256)
+k_face_range_bounds(const double2 *__restrict__ xy, const I *__restrict__ faces, int64_t f_begin,
+                    int64_t n, int k, unsigned long long *red) {
+    double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const I *face = faces + (f_begin + i) * k;
+        for (int j = 0; j < k; ++j) {
+            const I idx = face[j];
+            if (idx < 0) break;
+            const double2 p = xy[idx];
+            xmin = fmin(xmin, p.x); xmax = fmax(xmax, p.x);
+            ymin = fmin(ymin, p.y); ymax = fmax(ymax, p.y);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(red + 0, order_bits(xmin));
+        atomicMax(red + 1, order_bits(xmax));
+        atomicMin(red + 2, order_bits(ymin));
+        atomicMax(red + 3, order_bits(ymax));
     }
 }
 
@@ -303,13 +368,14 @@ k_reduce_level(const Box *__restrict__ child, int64_t n_child, Box *__restrict__
 template <typename I>
 static int launch_face_keys(const double2 *xy, const I *faces, int64_t f_begin, int64_t n, int k,
                             const double *frame, uint32_t *keys, int32_t *ids,
-                            unsigned long long *diag2, cudaStream_t s) {
+                            unsigned long long *diag2, const ClipBox &clip, unsigned long long *kept,
+                            cudaStream_t s) {
     if (n == 0) return XG_OK;
     const int B = 256;
     const unsigned G = (unsigned)div_up(n, B);
-    if (k <= 3) k_face_keys<I, 3><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2);
-    else if (k <= 4) k_face_keys<I, 4><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2);
-    else k_face_keys<I, XG_MAX_N_VERTEX><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2);
+    if (k <= 3) k_face_keys<I, 3><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept);
+    else if (k <= 4) k_face_keys<I, 4><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept);
+    else k_face_keys<I, XG_MAX_N_VERTEX><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept);
     XG_CHECK_LAUNCH();
     return XG_OK;
 }
@@ -344,11 +410,16 @@ static void ensure_pool_config() {
 
 int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
               int64_t f_end, int k, const double *d_frame, unsigned long long *d_diag2,
-              PackedMesh *out, cudaStream_t s) {
+              PackedMesh *out, cudaStream_t s, const double *h_clip_box, unsigned long long *d_kept) {
     ensure_pool_config();
     const int64_t n = f_end - f_begin;
     out->n = n;
     out->k = k;
+    ClipBox clip;
+    clip.on = (h_clip_box && d_kept) ? 1 : 0;
+    clip.xmin = clip.on ? h_clip_box[0] : 0.0; clip.xmax = clip.on ? h_clip_box[1] : 0.0;
+    clip.ymin = clip.on ? h_clip_box[2] : 0.0; clip.ymax = clip.on ? h_clip_box[3] : 0.0;
+    if (clip.on) XG_CUDA(cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), s));
     const double2 *xy = reinterpret_cast<const double2 *>(d_xy);
     DevBuf keys_in, keys_out, ids_in, tmp;
     XG_CUDA(keys_in.alloc(sizeof(uint32_t) * (size_t)n, s));
@@ -357,26 +428,34 @@ int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_
     int rc;
     if (idx_bytes == 4)
         rc = launch_face_keys<int32_t>(xy, (const int32_t *)d_faces, f_begin, n, k, d_frame,
-                                       keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, s);
+                                       keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, clip, d_kept, s);
     else
         rc = launch_face_keys<int64_t>(xy, (const int64_t *)d_faces, f_begin, n, k, d_frame,
-                                       keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, s);
+                                       keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, clip, d_kept, s);
     if (rc) return rc;
-    if (n > 0) {
+    int64_t n_pack = n;
+    if (clip.on) {
+        unsigned long long h_kept = 0;
+        XG_CUDA(cudaMemcpyAsync(&h_kept, d_kept, sizeof(h_kept), cudaMemcpyDeviceToHost, s));
+        XG_CUDA(cudaStreamSynchronize(s));
+        n_pack = (int64_t)h_kept;
+        out->n = n_pack;
+    }
+    if (n_pack > 0) {
         size_t tb = 0;
         XG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in.as<uint32_t>(),
                                                 keys_out.as<uint32_t>(), ids_in.as<int32_t>(),
-                                                out->perm, n, 0, 32, s));
+                                                out->perm, n_pack, 0, 32, s));
         XG_CUDA(tmp.alloc(tb, s));
         XG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys_in.as<uint32_t>(),
                                                 keys_out.as<uint32_t>(), ids_in.as<int32_t>(),
-                                                out->perm, n, 0, 32, s));
+                                                out->perm, n_pack, 0, 32, s));
     }
     if (idx_bytes == 4)
-        rc = launch_pack<int32_t>(xy, (const int32_t *)d_faces, k, out->perm, n, out->box,
+        rc = launch_pack<int32_t>(xy, (const int32_t *)d_faces, k, out->perm, n_pack, out->box,
                                   reinterpret_cast<double2 *>(out->poly), out->nvert, s);
     else
-        rc = launch_pack<int64_t>(xy, (const int64_t *)d_faces, k, out->perm, n, out->box,
+        rc = launch_pack<int64_t>(xy, (const int64_t *)d_faces, k, out->perm, n_pack, out->box,
                                   reinterpret_cast<double2 *>(out->poly), out->nvert, s);
     return rc;
 }
@@ -393,6 +472,12 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 extern "C" int xg_index_create(const double *d_xy, int64_t n_node, const void *d_faces,
                                int idx_bytes, int64_t n_face, int k, void *stream,
                                xg_index **out) {
+    return xg_index_create_clipped(d_xy, n_node, d_faces, idx_bytes, n_face, k, nullptr, stream, out);
+}
+
+extern "C" int xg_index_create_clipped(const double *d_xy, int64_t n_node, const void *d_faces,
+                                       int idx_bytes, int64_t n_face, int k,
+                                       const double *h_clip_box, void *stream, xg_index **out) {
     if (!out) { set_error("xg_index_create: out is NULL"); return XG_ERR_INVALID; }
     *out = nullptr;
     if (n_face < 0 || n_node < 0 || (idx_bytes != 4 && idx_bytes != 8) ||
@@ -460,12 +545,27 @@ extern "C" int xg_index_create(const double *d_xy, int64_t n_node, const void *d
         if (cudaGetLastError() != cudaSuccess) { rc = XG_ERR_CUDA; set_error("index: launch failed"); break; }
         PackedMesh pm;
         pm.perm = ix->perm; pm.box = ix->leaf_box; pm.poly = ix->poly; pm.nvert = ix->nvert;
-        rc = pack_mesh(d_xy, d_faces, idx_bytes, 0, n_face, k, d_frame, d_red + 4, &pm, s);
+        rc = pack_mesh(d_xy, d_faces, idx_bytes, 0, n_face, k, d_frame, d_red + 4, &pm, s, h_clip_box,
+                       d_red + 5);
         if (rc) break;
+        if (h_clip_box) {
+            // only the faces that can meet the box are indexed
+            ix->n_face = pm.n;
+            n_levels = 0;
+            int64_t c = pm.n;
+            while (pm.n > 0 && n_levels < MAX_LEVELS) {
+                c = div_up(c, FANOUT);
+                level_n[n_levels] = c;
+                ix->level_n[n_levels] = c;
+                ++n_levels;
+                if (c <= FANOUT) break;
+            }
+            ix->n_levels = n_levels;
+        }
         // tolerance needs the max diagonal, which k_face_keys has now reduced
         k_frame_from_red<<<1, 1, 0, s>>>(d_red, d_frame);
         const Box *child = ix->leaf_box;
-        int64_t n_child = n_face;
+        int64_t n_child = ix->n_face;
         for (int l = 0; l < n_levels; ++l) {
             const int64_t np = level_n[l];
             k_reduce_level<<<(unsigned)div_up(np * 32, 256), 256, 0, s>>>(child, n_child, ix->level_box[l], np);
@@ -486,6 +586,34 @@ extern "C" int xg_index_create(const double *d_xy, int64_t n_node, const void *d
         return rc;
     }
     *out = ix;
+    return XG_OK;
+}
+
+extern "C" int xg_face_range_bounds(const double *d_xy, const void *d_faces, int idx_bytes,
+                                    int64_t f_begin, int64_t f_end, int k, double h_box[4],
+                                    void *stream) {
+    if (!h_box || f_begin < 0 || f_end < f_begin || k < 3 || (idx_bytes != 4 && idx_bytes != 8)) {
+        set_error("xg_face_range_bounds: invalid argument");
+        return XG_ERR_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf red, frame;
+    XG_CUDA(red.alloc(sizeof(unsigned long long) * 8, s));
+    XG_CUDA(frame.alloc(sizeof(double) * 8, s));
+    k_init_red<<<1, 1, 0, s>>>(red.as<unsigned long long>());
+    const int64_t n = f_end - f_begin;
+    if (n > 0) {
+        if (idx_bytes == 4)
+            k_face_range_bounds<int32_t><<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)d_xy, (const int32_t *)d_faces,
+                                                                   f_begin, n, k, red.as<unsigned long long>());
+        else
+            k_face_range_bounds<int64_t><<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)d_xy, (const int64_t *)d_faces,
+                                                                   f_begin, n, k, red.as<unsigned long long>());
+    }
+    k_frame_from_red<<<1, 1, 0, s>>>(red.as<unsigned long long>(), frame.as<double>());
+    XG_CHECK_LAUNCH();
+    XG_CUDA(cudaMemcpyAsync(h_box, frame.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+    XG_CUDA(cudaStreamSynchronize(s));
     return XG_OK;
 }
 

@@ -17,8 +17,11 @@ struct PackedMesh {
 
 // d_frame: device pointer to [xmin, xmax, ymin, ymax] used to quantise the
 // Morton keys; d_diag2 (optional): running max of squared bbox diagonals.
+// h_clip_box + d_kept (optional): only faces whose bbox strictly intersects the
+// box are packed (out->n becomes their count; this synchronises the stream).
 int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
               int64_t f_end, int k, const double *d_frame, unsigned long long *d_diag2,
-              PackedMesh *out, cudaStream_t s);
+              PackedMesh *out, cudaStream_t s, const double *h_clip_box = nullptr,
+              unsigned long long *d_kept = nullptr);
 
 }  // namespace xg

@@ -63,3 +63,20 @@ def all_gather_columns(local: torch.Tensor, n_total: int, group: Optional[dist.P
         rb, re = shard_range(n_total, r, world)
         out[:, rb:re] = recv[r, :, : re - rb]
     return out
+
+
+def target_range_box(xy: torch.Tensor, faces: torch.Tensor, begin: int, end: int):
+    """(xmin, xmax, ymin, ymax) of the target faces [begin, end) (device tensors);
+    the clip box of a shard's source index."""
+    import ctypes
+
+    from . import _native
+
+    L = _native.lib()
+    box = (ctypes.c_double * 4)()
+    with torch.cuda.device(xy.device):
+        _native.check(
+            L.xg_face_range_bounds(_native.ptr(xy), _native.ptr(faces), faces.element_size(), int(begin),
+                                   int(end), int(faces.shape[1]), box, _native.stream_ptr())
+        )
+    return (box[0], box[1], box[2], box[3])

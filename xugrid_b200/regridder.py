@@ -107,9 +107,19 @@ class UnstructuredGrid2d:
     def overlap(self, other: "UnstructuredGrid2d", relative: bool,
                 target_range: Optional[Tuple[int, int]] = None) -> MatrixCSR:
         """unstructured.py:109-135 + sparse.py:119-127, as one device CSR."""
-        tree = self.ugrid_topology.celltree
         xy, faces = other.ugrid_topology.device_arrays()
         t_begin, t_end = (0, other.size) if target_range is None else target_range
+        if target_range is not None and (t_end - t_begin) < other.size and t_end > t_begin:
+            # a shard: index only the source faces its targets can touch
+            from .celltree import CellTree2d
+            from .distributed import target_range_box
+
+            sxy, sfaces = self.ugrid_topology.device_arrays()
+            tree = CellTree2d(sxy, sfaces, -1, device=sxy.device,
+                              clip_box=target_range_box(xy, faces, t_begin, t_end))
+        else:
+            tree = self.ugrid_topology.celltree
+        self.last_tree = tree
         indptr, indices, data = tree.intersect_faces_csr(
             xy, faces, -1, t_begin=t_begin, t_end=t_end, relative=relative
         )
