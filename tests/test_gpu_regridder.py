@@ -294,3 +294,30 @@ def test_barycentric_structured_source_known_answer(xb):
     assert np.allclose(out[0], [3.0, 3.0, 3.125, 3.375, 3.625, 3.875, 4.0, 4.0])
     assert np.allclose(out[-1], [1.0, 1.0, 1.125, 1.375, 1.625, 1.875, 2.0, 2.0])
     assert np.allclose(out[:, 0], [3.0, 3.0, 2.75, 2.25, 1.75, 1.25, 1.0, 1.0])
+
+
+def test_chunked_target_upload_gives_the_same_weights(xb):
+    """Targets of >= 2^20 faces are uploaded in face ranges and regridded range by
+    range while the next range is in flight; the CSR must not depend on that."""
+    sxy, sf = synthetic.jittered_lattice(300, 300, 41, "tri")
+    txy, tf = synthetic.jittered_lattice(740, 745, 42, "tri")
+    assert len(tf) >= 1 << 20
+    source = xb.Ugrid2d(sxy[:, 0], sxy[:, 1], -1, sf)
+    target = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf)
+    values = np.random.default_rng(5).random(len(sf))
+    r4 = xb.OverlapRegridder(source, target)
+    assert target._chunks is None or len(target._chunks) <= 4
+    out4 = r4.regrid(values)
+    w4 = r4._weights.to_numpy()
+    target.release_device()
+    source.release_device()
+    old = xb.OverlapRegridder._TARGET_CHUNKS
+    xb.OverlapRegridder._TARGET_CHUNKS = 1
+    try:
+        r1 = xb.OverlapRegridder(source, target)
+    finally:
+        xb.OverlapRegridder._TARGET_CHUNKS = old
+    w1 = r1._weights.to_numpy()
+    for a, b in zip(w4, w1):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out4, r1.regrid(values), equal_nan=True)

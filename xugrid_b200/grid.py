@@ -67,6 +67,8 @@ class Ugrid2d:
         self._xy_pin = None
         self._faces_pin = None
         self._ready = None
+        self._xy_ready = None
+        self._chunks = None
 
     # ---- basic properties -------------------------------------------------------
     @property
@@ -104,11 +106,13 @@ class Ugrid2d:
             return torch.device("cuda", torch.cuda.current_device())
         return torch.device(self.device)
 
-    def prefetch(self) -> None:
+    def prefetch(self, n_chunks: int = 1) -> None:
         """Start the host-to-device copy of the mesh on the side (copy) stream.
         The first call pins a host staging copy; later uploads (after
         ``release_device``) are asynchronous DMA transfers that overlap with
-        kernels on the compute stream."""
+        kernels on the compute stream.  With ``n_chunks > 1`` the connectivity
+        goes up in contiguous face ranges, each with its own event, so that a
+        consumer can start on the first range while the rest is in flight."""
         if self._xy_d is not None:
             return
         _native.lib()  # raises when there is no GPU: no CPU fallback
@@ -117,11 +121,26 @@ class Ugrid2d:
             self._xy_pin = torch.from_numpy(self.node_coordinates).pin_memory()
             self._faces_pin = torch.from_numpy(self.face_node_connectivity).pin_memory()
         copy_stream = _copy_stream(dev)
+        n = self.n_face
+        n_chunks = max(1, min(int(n_chunks), n)) if n > 0 else 1
+        bounds = [(n * c) // n_chunks for c in range(n_chunks + 1)]
         with torch.cuda.stream(copy_stream):
             self._xy_d = self._xy_pin.to(dev, non_blocking=True)
-            self._faces_d = self._faces_pin.to(dev, non_blocking=True)
-            self._ready = torch.cuda.Event()
-            self._ready.record(copy_stream)
+            self._xy_ready = torch.cuda.Event()
+            self._xy_ready.record(copy_stream)
+            self._faces_d = torch.empty(self._faces_pin.shape, dtype=self._faces_pin.dtype, device=dev)
+            self._chunks = []
+            for b, e in zip(bounds[:-1], bounds[1:]):
+                self._faces_d[b:e].copy_(self._faces_pin[b:e], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                self._chunks.append((b, e, ev))
+            self._ready = self._chunks[-1][2] if self._chunks else self._xy_ready
+
+    def _adopt(self, cur) -> None:
+        # tensors were allocated on the copy stream: tell the allocator who uses them
+        self._xy_d.record_stream(cur)
+        self._faces_d.record_stream(cur)
 
     def device_arrays(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """(n_node, 2) float64 and (n_face, k) int tensors in HBM (cached)."""
@@ -129,10 +148,28 @@ class Ugrid2d:
         if self._ready is not None:
             cur = torch.cuda.current_stream(self._xy_d.device)
             cur.wait_event(self._ready)
-            self._xy_d.record_stream(cur)
-            self._faces_d.record_stream(cur)
+            self._adopt(cur)
             self._ready = None
+            self._chunks = None
         return self._xy_d, self._faces_d
+
+    def device_chunks(self):
+        """(xy, faces, [(begin, end)]) with the compute stream made to wait only
+        for the coordinates; call ``wait_chunk(i)`` before using face range i.
+        None when the mesh is already fully resident."""
+        self.prefetch()
+        if self._ready is None or not self._chunks or len(self._chunks) < 2:
+            return None
+        cur = torch.cuda.current_stream(self._xy_d.device)
+        cur.wait_event(self._xy_ready)
+        self._adopt(cur)
+        return self._xy_d, self._faces_d, [(b, e) for b, e, _ in self._chunks]
+
+    def wait_chunk(self, i: int) -> None:
+        cur = torch.cuda.current_stream(self._xy_d.device)
+        cur.wait_event(self._chunks[i][2])
+        if i == len(self._chunks) - 1:
+            self._ready = None
 
     def release_device(self) -> None:
         """Drop the device mirrors and the spatial index (the pinned host
@@ -141,6 +178,8 @@ class Ugrid2d:
         self._xy_d = None
         self._faces_d = None
         self._ready = None
+        self._xy_ready = None
+        self._chunks = None
 
     @property
     def celltree(self) -> CellTree2d:

@@ -107,6 +107,23 @@ class UnstructuredGrid2d:
     def overlap(self, other: "UnstructuredGrid2d", relative: bool,
                 target_range: Optional[Tuple[int, int]] = None) -> MatrixCSR:
         """unstructured.py:109-135 + sparse.py:119-127, as one device CSR."""
+        chunks = other.ugrid_topology.device_chunks() if target_range is None else None
+        if chunks is not None:
+            # the target connectivity is still arriving in face ranges: overlap the
+            # weights of range c with the transfer of range c + 1
+            xy, faces, ranges = chunks
+            tree = self.ugrid_topology.celltree
+            self.last_tree = tree
+            parts, offset = [], 0
+            for c, (b, e) in enumerate(ranges):
+                other.ugrid_topology.wait_chunk(c)
+                ip, ix, dt = tree.intersect_faces_csr(xy, faces, -1, t_begin=b, t_end=e, relative=relative)
+                parts.append((ip[1:] + offset if c else ip + offset, ix, dt))
+                offset += int(dt.numel())
+            indptr = torch.cat([p[0] for p in parts])
+            indices = torch.cat([p[1] for p in parts])
+            data = torch.cat([p[2] for p in parts])
+            return MatrixCSR(data, indices, indptr, other.size, self.size, int(data.numel()))
         xy, faces = other.ugrid_topology.device_arrays()
         t_begin, t_end = (0, other.size) if target_range is None else target_range
         if target_range is not None and (t_end - t_begin) < other.size and t_end > t_begin:
@@ -236,6 +253,7 @@ def _grid_from_dataset(ds: dict, prefix: str):
 
 class BaseRegridder(abc.ABC):
     _METHODS: Tuple[str, ...] = ()
+    _TARGET_CHUNKS = 4  # face ranges a large target mesh is uploaded in
 
     def __init__(self, source, target, tolerance: Optional[float] = None,
                  target_range: Optional[Tuple[int, int]] = None):
@@ -245,8 +263,9 @@ class BaseRegridder(abc.ABC):
         self._target_range = target_range
         # start both uploads on the copy stream: the index build over the source
         # overlaps with the transfer of the target
-        for side in (self._source, self._target):
-            side.to_unstructured().ugrid_topology.prefetch()
+        self._source.to_unstructured().ugrid_topology.prefetch()
+        tgt_grid = self._target.to_unstructured().ugrid_topology
+        tgt_grid.prefetch(n_chunks=self._TARGET_CHUNKS if tgt_grid.n_face >= (1 << 20) else 1)
         self._compute_weights(self._source, self._target, tolerance)
 
     # ---- method selection (regridder.py:124-141) --------------------------------------
