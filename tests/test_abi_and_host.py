@@ -109,5 +109,6 @@ def test_shard_range_partitions_exactly():
             for (a, b), (c, d) in zip(ranges[:-1], ranges[1:]):
                 assert b == c
             assert max(b - a for a, b in ranges) == max_shard(n, world) or n == 0
+            assert all(a == min(n, r * max_shard(n, world)) for r, (a, _) in enumerate(ranges))
     with pytest.raises(ValueError):
         shard_range(10, 2, 2)

@@ -20,13 +20,13 @@ import torch.distributed as dist
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
-    """Contiguous, balanced [begin, end) of n items for `rank` of `world`;
-    the first n % world ranks get one extra item."""
+    """Contiguous [begin, end) of n items for `rank` of `world`: every rank owns
+    ceil(n / world) items except the last ones, which own what is left.  Equal
+    strides make the gathered output contiguous (see all_gather_columns)."""
     if world <= 0 or not (0 <= rank < world):
         raise ValueError("invalid rank/world")
-    base, rem = divmod(n, world)
-    begin = rank * base + min(rank, rem)
-    return begin, begin + base + (1 if rank < rem else 0)
+    c = max_shard(n, world)
+    return min(n, rank * c), min(n, (rank + 1) * c)
 
 
 def max_shard(n: int, world: int) -> int:
@@ -38,8 +38,10 @@ def all_gather_columns(local: torch.Tensor, n_total: int, group: Optional[dist.P
     """
     ``local`` is this rank's (n_extra, rows_local) block of columns
     ``shard_range(n_total, rank, world)``.  Returns the full (n_extra, n_total)
-    array on every rank with ONE all_gather_into_tensor of equally sized,
-    padded slabs laid out [rank][n_extra][max_shard].
+    array on every rank with ONE all_gather_into_tensor of equally sized slabs
+    laid out [rank][n_extra][max_shard].  Because every shard starts at a
+    multiple of max_shard, a single time step (n_extra == 1) comes back as a
+    contiguous view of the receive buffer, without any reassembly copy.
     """
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local if out is None else out.copy_(local)
@@ -50,19 +52,17 @@ def all_gather_columns(local: torch.Tensor, n_total: int, group: Optional[dist.P
     b, e = shard_range(n_total, rank, world)
     if local.shape[1] != e - b:
         raise ValueError(f"rank {rank} holds {local.shape[1]} columns, expected {e - b}")
-    send = local.new_empty((n_extra, pad))
-    send[:, : e - b] = local
-    if e - b < pad:
-        send[:, e - b :] = 0
+    if e - b == pad and local.is_contiguous():
+        send = local
+    else:
+        send = local.new_zeros((n_extra, pad))
+        send[:, : e - b] = local
     recv = local.new_empty((world * n_extra, pad))  # concatenation along dim 0
     dist.all_gather_into_tensor(recv, send, group=group)
-    recv = recv.view(world, n_extra, pad)
-    if out is None:
-        out = local.new_empty((n_extra, n_total))
-    for r in range(world):
-        rb, re = shard_range(n_total, r, world)
-        out[:, rb:re] = recv[r, :, : re - rb]
-    return out
+    full = recv.view(world, n_extra, pad).permute(1, 0, 2).reshape(n_extra, world * pad)[:, :n_total]
+    if out is not None:
+        return out.copy_(full)
+    return full
 
 
 def target_range_box(xy: torch.Tensor, faces: torch.Tensor, begin: int, end: int):
