@@ -381,6 +381,20 @@ def test_overlap_dense_sources_rerun_path(xb):
     assert np.array_equal(np.lexsort((indices, rows)), np.arange(len(indices)))
 
 
+@pytest.mark.parametrize("n_coarse,min_row", [(6, 17), (1, 1025)])
+def test_overlap_long_rows_are_sorted(xb, n_coarse, min_row):
+    """rows longer than the register networks (warp rank sort in shared memory) and
+    longer than its capacity (one target covering thousands of source faces)"""
+    sxy, sf = synthetic.jittered_lattice(48, 48, 41, "tri")
+    txy, tf = synthetic.jittered_lattice(n_coarse, n_coarse, 42, "quad", jitter=0.0, bounds=(0.01, 0.99, 0.01, 0.99))
+    g, tree = gpu_triplets(xb, sxy, sf, txy, tf)
+    assert_same_triplets(g, oracle_triplets(sxy, sf, txy, tf))
+    indptr, indices, _ = (t.cpu().numpy() for t in tree.intersect_faces_csr(txy, tf))
+    assert np.diff(indptr).max() >= min_row
+    rows = np.repeat(np.arange(len(tf)), np.diff(indptr))
+    assert np.array_equal(np.lexsort((indices, rows)), np.arange(len(indices)))
+
+
 def test_clipped_index_equals_full_index_on_a_target_range(xb):
     from xugrid_b200.distributed import shard_range, target_range_box
 

@@ -42,7 +42,7 @@ constexpr int TRAV_QFLUSH = 96;   // flush threshold (a child test adds <= 32)
 constexpr int PAIRS_PER_TARGET_GUESS = 16;
 
 // device counters of one job
-enum { CTR_VISITS = 0, CTR_TESTS = 1, CTR_PAIRS = 2, CTR_SURV = 3, CTR_N = 8 };
+enum { CTR_VISITS = 0, CTR_TESTS = 1, CTR_PAIRS = 2, CTR_SURV = 3, CTR_LONG = 6, CTR_N = 8 };
 
 struct TraverseParams {
     const Box *boxes[MAX_LEVELS + 1];  // [0] = leaves, [d] = node level d-1
@@ -220,7 +220,7 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
                  const double2 *__restrict__ tpoly, const uint8_t *__restrict__ tnv, int kt,
                  const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks,
                  const int32_t *__restrict__ tperm, int64_t t_begin, double *__restrict__ area,
-                 int32_t *__restrict__ row_cnt) {
+                 int2 *__restrict__ dest, int32_t *__restrict__ row_cnt) {
     extern __shared__ double2 s_buf[];
     const unsigned long long n_surv = ctr[CTR_SURV];
     double2 *bufA = s_buf + threadIdx.x;
@@ -228,6 +228,7 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
     for (unsigned long long q = (unsigned long long)blockIdx.x * BT + threadIdx.x; q < n_surv;
          q += (unsigned long long)gridDim.x * BT) {
         const int2 r = surv[q];
+        const int32_t row = tperm[r.x] - (int32_t)t_begin;  // issued with the polygon loads
         double2 a[KT], b[KS];
         const int na = load_poly<KT>(tpoly, tnv, r.x, kt, a);
         const int nb = load_poly<KS>(spoly, snv, r.y, ks, b);
@@ -239,9 +240,15 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
         } else {
             ar = clip_area<KT, KS>(a, na, b, nb, bufA, bufB, BT);
         }
-        if (!(ar > 0.0)) ar = 0.0;
-        area[q] = ar;
-        if (ar > 0.0) atomicAdd(row_cnt + (tperm[r.x] - t_begin), 1);
+        // a positive area takes the next free slot of its row here, so that the
+        // scatter pass needs no atomic and only one level of gathers
+        int2 d = make_int2(-1, 0);
+        if (ar > 0.0) {
+            d.x = row;
+            d.y = atomicAdd(row_cnt + row, 1);
+            area[q] = ar;
+        }
+        dest[q] = d;
     }
 }
 
@@ -263,24 +270,23 @@ __device__ __forceinline__ double packed_face_area(const double2 *__restrict__ p
     return 0.5 * fabs(det);
 }
 
-// one thread per survivor: a positive area takes the next free slot of its row
-// (row_cnt counts down, so the row fills from the back; k_sort_rows orders it)
+// one thread per survivor with a positive area: entry -> indptr[row] + slot (both
+// resolved by k_clip_survivors; k_sort_rows orders the row afterwards)
 __global__ void __launch_bounds__(256)
-k_scatter(const int2 *__restrict__ surv, const double *__restrict__ area, unsigned long long n_surv,
-          const int32_t *__restrict__ tperm, int64_t t_begin, const int32_t *__restrict__ sperm,
+k_scatter(const int2 *__restrict__ surv, const double *__restrict__ area, const int2 *__restrict__ dest,
+          unsigned long long n_surv, const int32_t *__restrict__ sperm,
           const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks, int relative,
-          const int64_t *__restrict__ indptr, int32_t *__restrict__ row_cnt,
-          int32_t *__restrict__ indices, double *__restrict__ data) {
+          const int64_t *__restrict__ indptr, int32_t *__restrict__ indices, double *__restrict__ data) {
     for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n_surv;
          q += (unsigned long long)gridDim.x * blockDim.x) {
+        const int2 d = dest[q];
+        if (d.x < 0) continue;
+        const int32_t sy = surv[q].y;
         double a = area[q];
-        if (!(a > 0.0)) continue;
-        const int2 r = surv[q];
-        const int64_t row = tperm[r.x] - t_begin;
-        const int slot = atomicSub(row_cnt + row, 1) - 1;
-        const int64_t pos = indptr[row] + slot;
-        if (relative) a = a / packed_face_area(spoly + (int64_t)r.y * ks, snv[r.y]);
-        indices[pos] = sperm[r.y];
+        const int64_t pos = indptr[d.x] + d.y;
+        const int32_t col = sperm[sy];
+        if (relative) a = a / packed_face_area(spoly + (int64_t)sy * ks, snv[sy]);
+        indices[pos] = col;
         data[pos] = a;
     }
 }
@@ -295,54 +301,127 @@ __device__ __forceinline__ void cswap(int32_t &ka, double &va, int32_t &kb, doub
     va = tv;
 }
 
-// one thread per row: ascending source index.  Rows of up to 8 entries (the
-// common case) are sorted in registers with a fixed network; longer rows fall
-// back to an in-place insertion sort.
+// Batcher odd-even merge sort networks over register-resident (key, value)
+// slots (19 / 63 comparators; generated and checked with the 0-1 principle)
+#define XG_CS(i, j) cswap(k[i], v[i], k[j], v[j])
+__device__ __forceinline__ void sort_network(int32_t (&k)[8], double (&v)[8]) {
+    XG_CS(0, 1); XG_CS(2, 3); XG_CS(4, 5); XG_CS(6, 7); XG_CS(0, 2); XG_CS(1, 3); XG_CS(4, 6); XG_CS(5, 7);
+    XG_CS(1, 2); XG_CS(5, 6); XG_CS(0, 4); XG_CS(1, 5); XG_CS(2, 6); XG_CS(3, 7); XG_CS(2, 4); XG_CS(3, 5);
+    XG_CS(1, 2); XG_CS(3, 4); XG_CS(5, 6);
+}
+__device__ __forceinline__ void sort_network(int32_t (&k)[16], double (&v)[16]) {
+    XG_CS(0, 1); XG_CS(2, 3); XG_CS(4, 5); XG_CS(6, 7); XG_CS(8, 9); XG_CS(10, 11); XG_CS(12, 13); XG_CS(14, 15);
+    XG_CS(0, 2); XG_CS(1, 3); XG_CS(4, 6); XG_CS(5, 7); XG_CS(8, 10); XG_CS(9, 11); XG_CS(12, 14); XG_CS(13, 15);
+    XG_CS(1, 2); XG_CS(5, 6); XG_CS(9, 10); XG_CS(13, 14);
+    XG_CS(0, 4); XG_CS(1, 5); XG_CS(2, 6); XG_CS(3, 7); XG_CS(8, 12); XG_CS(9, 13); XG_CS(10, 14); XG_CS(11, 15);
+    XG_CS(2, 4); XG_CS(3, 5); XG_CS(10, 12); XG_CS(11, 13);
+    XG_CS(1, 2); XG_CS(3, 4); XG_CS(5, 6); XG_CS(9, 10); XG_CS(11, 12); XG_CS(13, 14);
+    XG_CS(0, 8); XG_CS(1, 9); XG_CS(2, 10); XG_CS(3, 11); XG_CS(4, 12); XG_CS(5, 13); XG_CS(6, 14); XG_CS(7, 15);
+    XG_CS(4, 8); XG_CS(5, 9); XG_CS(6, 10); XG_CS(7, 11);
+    XG_CS(2, 4); XG_CS(3, 5); XG_CS(6, 8); XG_CS(7, 9); XG_CS(10, 12); XG_CS(11, 13);
+    XG_CS(1, 2); XG_CS(3, 4); XG_CS(5, 6); XG_CS(7, 8); XG_CS(9, 10); XG_CS(11, 12); XG_CS(13, 14);
+}
+#undef XG_CS
+
+template <int N>
+__device__ __forceinline__ void sort_row_regs(int64_t b, int n, int32_t *__restrict__ indices,
+                                              double *__restrict__ data) {
+    int32_t k[N];
+    double v[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        k[i] = i < n ? indices[b + i] : 0x7fffffff;
+        v[i] = i < n ? data[b + i] : 0.0;
+    }
+    sort_network(k, v);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (i < n) {
+            indices[b + i] = k[i];
+            data[b + i] = v[i];
+        }
+}
+
+constexpr int SORT_SHORT = 16;     // rows up to this length are sorted by one thread in registers
+constexpr int SORT_LONG_CAP = 1024;  // rows up to this length are rank-sorted by one warp in shared memory
+
+// one thread per row: ascending source index.  Short rows (the common case at
+// comparable resolutions) go through a fixed network in registers, warp-uniformly
+// (8 or 16 slots by the longest row of the warp); longer rows are queued for
+// k_sort_long_rows.
 __global__ void __launch_bounds__(256)
 k_sort_rows(const int64_t *__restrict__ indptr, int64_t n_rows, int32_t *__restrict__ indices,
-            double *__restrict__ data) {
+            double *__restrict__ data, int32_t *__restrict__ long_rows,
+            unsigned long long *__restrict__ n_long) {
     const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (row >= n_rows) return;
-    const int64_t b = indptr[row];
-    const int n = (int)(indptr[row + 1] - b);
-    if (n < 2) return;
-    if (n <= 8) {
-        int32_t k[8];
-        double v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            k[i] = i < n ? indices[b + i] : 0x7fffffff;
-            v[i] = i < n ? data[b + i] : 0.0;
-        }
-        // 19-comparator network for 8 keys
-#define XG_CS(i, j) cswap(k[i], v[i], k[j], v[j])
-        XG_CS(0, 1); XG_CS(2, 3); XG_CS(4, 5); XG_CS(6, 7);
-        XG_CS(0, 2); XG_CS(1, 3); XG_CS(4, 6); XG_CS(5, 7);
-        XG_CS(1, 2); XG_CS(5, 6); XG_CS(0, 4); XG_CS(3, 7);
-        XG_CS(1, 5); XG_CS(2, 6);
-        XG_CS(1, 4); XG_CS(3, 6);
-        XG_CS(2, 4); XG_CS(3, 5);
-        XG_CS(3, 4);
-#undef XG_CS
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (i < n) {
-                indices[b + i] = k[i];
-                data[b + i] = v[i];
-            }
-        return;
+    int64_t b = 0;
+    int n = 0;
+    if (row < n_rows) {
+        b = indptr[row];
+        n = (int)min((int64_t)0x7fffffff, indptr[row + 1] - b);
     }
-    for (int i = 1; i < n; ++i) {
-        const int32_t key = indices[b + i];
-        const double val = data[b + i];
-        int j = i - 1;
-        while (j >= 0 && indices[b + j] > key) {
-            indices[b + j + 1] = indices[b + j];
-            data[b + j + 1] = data[b + j];
-            --j;
+    const bool is_long = n > SORT_SHORT;
+    const unsigned lm = __ballot_sync(0xffffffffu, is_long);
+    if (lm) {
+        const int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == __ffs(lm) - 1) base = atomicAdd(n_long, (unsigned long long)__popc(lm));
+        base = __shfl_sync(0xffffffffu, base, __ffs(lm) - 1);
+        if (is_long) long_rows[base + __popc(lm & ((1u << lane) - 1u))] = (int32_t)row;
+    }
+    const int ns = is_long ? 0 : n;
+    const bool wide = __any_sync(0xffffffffu, ns > 8);
+    if (wide) {
+        if (ns >= 2) sort_row_regs<16>(b, ns, indices, data);
+    } else {
+        if (ns >= 2) sort_row_regs<8>(b, ns, indices, data);
+    }
+}
+
+// one warp per queued row: rank sort through shared memory (source indices of a
+// row are distinct, so the rank of a key is its final position)
+__global__ void __launch_bounds__(128)
+k_sort_long_rows(const int64_t *__restrict__ indptr, const int32_t *__restrict__ long_rows,
+                 const unsigned long long *__restrict__ n_long, int32_t *__restrict__ indices,
+                 double *__restrict__ data) {
+    __shared__ int32_t s_key[4][SORT_LONG_CAP];
+    __shared__ double s_val[4][SORT_LONG_CAP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long total = *n_long;
+    for (unsigned long long r = (unsigned long long)blockIdx.x * 4 + w; r < total;
+         r += (unsigned long long)gridDim.x * 4) {
+        const int64_t row = long_rows[r];
+        const int64_t b = indptr[row];
+        const int64_t n = indptr[row + 1] - b;
+        if (n <= SORT_LONG_CAP) {
+            for (int i = lane; i < n; i += 32) {
+                s_key[w][i] = indices[b + i];
+                s_val[w][i] = data[b + i];
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                const int32_t key = s_key[w][i];
+                int rank = 0;
+                for (int j = 0; j < (int)n; ++j) rank += s_key[w][j] < key ? 1 : 0;
+                indices[b + rank] = key;
+                data[b + rank] = s_val[w][i];
+            }
+            __syncwarp();
+        } else if (lane == 0) {
+            // beyond any mesh pair seen in practice: in-place insertion sort
+            for (int64_t i = 1; i < n; ++i) {
+                const int32_t key = indices[b + i];
+                const double val = data[b + i];
+                int64_t j = i - 1;
+                while (j >= 0 && indices[b + j] > key) {
+                    indices[b + j + 1] = indices[b + j];
+                    data[b + j + 1] = data[b + j];
+                    --j;
+                }
+                indices[b + j + 1] = key;
+                data[b + j + 1] = val;
+            }
         }
-        indices[b + j + 1] = key;
-        data[b + j + 1] = val;
     }
 }
 
@@ -364,6 +443,7 @@ struct ClipArgs {
     const int32_t *tperm;
     int64_t t_begin;
     double *area;
+    int2 *dest;
     int32_t *row_cnt;
     cudaEvent_t between;  // recorded between the two kernels (phase timing)
 };
@@ -384,7 +464,7 @@ static int launch_clip(const ClipArgs &A, cudaStream_t s) {
     if (per_sm < 1) per_sm = 1;
     kern<<<NUM_SMS * per_sm, BT, smem, s>>>(A.surv, A.ctr, (const double2 *)A.tpoly, A.tnv, A.kt,
                                             (const double2 *)A.spoly, A.snv, A.ks, A.tperm, A.t_begin,
-                                            A.area, A.row_cnt);
+                                            A.area, A.dest, A.row_cnt);
     XG_CHECK_LAUNCH();
     return XG_OK;
 }
@@ -458,6 +538,7 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
     A.surv = job->surv.as<int2>(); A.ctr = job->ctr.as<unsigned long long>();
     A.tperm = job->tperm.as<int32_t>(); A.t_begin = job->t_begin;
     A.area = job->area.as<double>(); A.row_cnt = job->row_cnt.as<int32_t>();
+    A.dest = job->pairs.as<int2>();  // the candidate arena is dead once k_sat has run
     if (!job->ev[job->n_ev]) XG_CUDA(cudaEventCreate(&job->ev[job->n_ev]));
     A.between = job->ev[job->n_ev++];  // XG_PHASE_CLIP starts between the two kernels
     int rc;
@@ -573,10 +654,15 @@ extern "C" int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32
         if (!d_indices || !d_area || !d_indptr) { set_error("xg_overlap_finish: NULL output"); delete job; return XG_ERR_INVALID; }
         const xg_index *src = job->src;
         k_scatter<<<NUM_SMS * 8, 256, 0, s>>>(
-            job->surv.as<int2>(), job->area.as<double>(), (unsigned long long)job->n_surv,
-            job->tperm.as<int32_t>(), job->t_begin, src->perm, (const double2 *)src->poly, src->nvert,
-            src->k, relative, d_indptr, job->row_cnt.as<int32_t>(), d_indices, d_area);
-        k_sort_rows<<<(unsigned)div_up(job->n_t, 256), 256, 0, s>>>(d_indptr, job->n_t, d_indices, d_area);
+            job->surv.as<int2>(), job->area.as<double>(), job->pairs.as<int2>(),
+            (unsigned long long)job->n_surv, src->perm, (const double2 *)src->poly, src->nvert, src->k,
+            relative, d_indptr, d_indices, d_area);
+        // rows longer than SORT_SHORT are queued in the (now dead) target box buffer
+        unsigned long long *n_long = job->ctr.as<unsigned long long>() + CTR_LONG;
+        int32_t *long_rows = job->tbox.as<int32_t>();
+        k_sort_rows<<<(unsigned)div_up(job->n_t, 256), 256, 0, s>>>(d_indptr, job->n_t, d_indices, d_area,
+                                                                   long_rows, n_long);
+        k_sort_long_rows<<<NUM_SMS * 4, 128, 0, s>>>(d_indptr, long_rows, n_long, d_indices, d_area);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = cuda_fail(e, "k_scatter/k_sort_rows", __FILE__, __LINE__);
     }
