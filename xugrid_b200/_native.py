@@ -15,7 +15,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libxgregrid.so")
+# XG_LIB_PATH selects a tuning build of the same library (development only)
+LIB_PATH = os.environ.get("XG_LIB_PATH") or os.path.join(_HERE, "_lib", "libxgregrid.so")
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64

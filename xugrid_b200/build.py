@@ -50,7 +50,14 @@ def needs_build() -> bool:
     return not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < _deps_mtime()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    """variant/defines: tuning builds (`--variant NAME -DFOO=1`) go to
+    _lib/libxgregrid_NAME.so and are selected with XG_LIB_PATH (development only)."""
+    global BUILD, LIB_PATH
+    if variant:
+        BUILD = os.path.join(HERE, "_build", variant)
+        LIB_PATH = os.path.join(LIB_DIR, f"libxgregrid_{variant}.so")
+        force = True
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(BUILD, exist_ok=True)
@@ -70,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             and os.path.getmtime(obj) > max(os.path.getmtime(srcp), headers_mtime)
         ):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-c", srcp, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", srcp, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -92,5 +99,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=variant,
+                 defines=[a for a in sys.argv if a.startswith("-D")])
     print(path)

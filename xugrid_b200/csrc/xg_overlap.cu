@@ -169,9 +169,9 @@ __device__ __noinline__ double clip_area_fallback(const double2 *pa, int na, con
                                                   double2 *bufA, double2 *bufB, int stride) {
     double2 a[KT], b[KS];
 #pragma unroll
-    for (int i = 0; i < KT; ++i) a[i] = pa[i];
+    for (int i = 0; i < KT; ++i) a[i] = i < na ? pa[i] : make_double2(0.0, 0.0);
 #pragma unroll
-    for (int i = 0; i < KS; ++i) b[i] = pb[i];
+    for (int i = 0; i < KS; ++i) b[i] = i < nb ? pb[i] : make_double2(0.0, 0.0);
     return clip_area<KT, KS>(a, na, b, nb, bufA, bufB, stride);
 }
 
@@ -214,41 +214,103 @@ k_sat(const int2 *__restrict__ pairs, unsigned long long cap, const double2 *__r
     }
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS); completion is awaited with
+// cp_async_wait_all() by the issuing thread
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// loads whose position in the instruction stream matters (software pipelining):
+// a volatile asm is not moved across the other volatile asms around it
+__device__ __forceinline__ int2 ld_int2_here(const int2 *p) {
+    int2 v;
+    asm volatile("ld.global.nc.v2.s32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void schedule_fence() { asm volatile("" ::: "memory"); }
+
+// One thread per survivor, grid-stride.  The kernel is bound by the latency of
+// the polygon gathers (ncu: long-scoreboard stalls were half of all samples with
+// 24 warps per SM), so the polygons of the NEXT survivor of a thread are staged
+// into its shared-memory slots with cp.async while the current one is clipped,
+// and the survivor record after that is already in flight to a register.
+// Shared memory per thread: two (KT+KS)-vertex ping-pong lists + one staged pair.
 template <int KT, int KS, int BT, int MINB>
 __global__ void __launch_bounds__(BT, MINB)
 k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__restrict__ ctr,
                  const double2 *__restrict__ tpoly, const uint8_t *__restrict__ tnv, int kt,
                  const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks,
-                 const int32_t *__restrict__ tperm, int64_t t_begin, double *__restrict__ area,
-                 int2 *__restrict__ dest, int32_t *__restrict__ row_cnt) {
+                 double *__restrict__ area, int32_t *__restrict__ pos_cnt) {
     extern __shared__ double2 s_buf[];
+    constexpr int M = KT + KS;
     const unsigned long long n_surv = ctr[CTR_SURV];
     double2 *bufA = s_buf + threadIdx.x;
-    double2 *bufB = s_buf + (size_t)(KT + KS) * BT + threadIdx.x;
-    for (unsigned long long q = (unsigned long long)blockIdx.x * BT + threadIdx.x; q < n_surv;
-         q += (unsigned long long)gridDim.x * BT) {
-        const int2 r = surv[q];
-        const int32_t row = tperm[r.x] - (int32_t)t_begin;  // issued with the polygon loads
+    double2 *bufB = s_buf + (size_t)M * BT + threadIdx.x;
+    double2 *stg = s_buf + (size_t)2 * M * BT + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * BT;
+    unsigned long long q = (unsigned long long)blockIdx.x * BT + threadIdx.x;
+
+    auto stage = [&](const int2 r) {
+        const double2 *tp = tpoly + (int64_t)r.x * kt;
+        const double2 *sp = spoly + (int64_t)r.y * ks;
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+            if (j < kt) cp_async16(stg + j * BT, tp + j);
+#pragma unroll
+        for (int j = 0; j < KS; ++j)
+            if (j < ks) cp_async16(stg + (KT + j) * BT, sp + j);
+    };
+
+    // loop-carried pipeline registers: r / na / nb describe the STAGED survivor,
+    // r_next the one after it
+    int2 r = make_int2(0, 0), r_next = make_int2(0, 0);
+    int na = 3, nb = 3;  // vertex counts (looked up for K > 3 only)
+    if (q < n_surv) {
+        r = surv[q];
+        stage(r);
+        if (KT > 3) na = tnv[r.x] & 0x7f;
+        if (KS > 3) nb = snv[r.y] & 0x7f;
+    }
+    if (q + stride < n_surv) r_next = surv[q + stride];
+    for (; q < n_surv; q += stride) {
+        cp_async_wait_all();
         double2 a[KT], b[KS];
-        const int na = load_poly<KT>(tpoly, tnv, r.x, kt, a);
-        const int nb = load_poly<KS>(spoly, snv, r.y, ks, b);
+#pragma unroll
+        for (int j = 0; j < KT; ++j) a[j] = stg[j * BT];
+#pragma unroll
+        for (int j = 0; j < KS; ++j) b[j] = stg[(KT + j) * BT];
+        const int2 r_cur = r;
+        const int na_cur = na, nb_cur = nb;
+        // ---- prefetch
+        if (q + stride < n_surv) {
+            r = r_next;
+            stage(r);
+            if (KT > 3) na = tnv[r.x] & 0x7f;
+            if (KS > 3) nb = snv[r.y] & 0x7f;
+        }
+        if (q + 2 * stride < n_surv) r_next = ld_int2_here(surv + q + 2 * stride);
+        schedule_fence();
+        // ---- clip
         double ar;
         if (KT + KS <= 32) {
             bool fb = false;
-            ar = clip_area_dense<KT, KS>(a, na, b, nb, bufA, bufB, BT, &fb);
-            if (fb) ar = clip_area_fallback<KT, KS>(a, na, b, nb, bufA, bufB, BT);
+#ifdef XG_CLIP_DENSE
+            ar = clip_area_dense<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT, &fb);
+#else
+            ar = clip_area_masks<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT, &fb);
+#endif
+            if (fb)
+                ar = clip_area_fallback<KT, KS>(tpoly + (int64_t)r_cur.x * kt, na_cur,
+                                                spoly + (int64_t)r_cur.y * ks, nb_cur, bufA, bufB, BT);
         } else {
-            ar = clip_area<KT, KS>(a, na, b, nb, bufA, bufB, BT);
+            ar = clip_area<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT);
         }
-        // a positive area takes the next free slot of its row here, so that the
-        // scatter pass needs no atomic and only one level of gathers
-        int2 d = make_int2(-1, 0);
-        if (ar > 0.0) {
-            d.x = row;
-            d.y = atomicAdd(row_cnt + row, 1);
-            area[q] = ar;
-        }
-        dest[q] = d;
+        if (!(ar > 0.0)) ar = 0.0;
+        area[q] = ar;
+        // entries per target, counted by SORTED target position (fire-and-forget)
+        if (ar > 0.0) atomicAdd(pos_cnt + r_cur.x, 1);
     }
 }
 
@@ -270,23 +332,34 @@ __device__ __forceinline__ double packed_face_area(const double2 *__restrict__ p
     return 0.5 * fabs(det);
 }
 
-// one thread per survivor with a positive area: entry -> indptr[row] + slot (both
-// resolved by k_clip_survivors; k_sort_rows orders the row afterwards)
+// rows are counted by sorted target position; the row pointer is in the caller's
+// row order: cnt_row[tperm[t] - t_begin] = pos_cnt[t]
 __global__ void __launch_bounds__(256)
-k_scatter(const int2 *__restrict__ surv, const double *__restrict__ area, const int2 *__restrict__ dest,
-          unsigned long long n_surv, const int32_t *__restrict__ sperm,
+k_counts_to_rows(const int32_t *__restrict__ pos_cnt, const int32_t *__restrict__ tperm, int64_t t_begin,
+                 int64_t n_t, int32_t *__restrict__ cnt_row) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n_t) cnt_row[tperm[t] - t_begin] = pos_cnt[t];
+    if (t == 0) cnt_row[n_t] = 0;
+}
+
+// one thread per survivor: a positive area takes the next free slot of its row
+// (pos_cnt counts down, so the row fills from the back; k_sort_rows orders it)
+__global__ void __launch_bounds__(256)
+k_scatter(const int2 *__restrict__ surv, const double *__restrict__ area, unsigned long long n_surv,
+          const int32_t *__restrict__ tperm, int64_t t_begin, const int32_t *__restrict__ sperm,
           const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks, int relative,
-          const int64_t *__restrict__ indptr, int32_t *__restrict__ indices, double *__restrict__ data) {
+          const int64_t *__restrict__ indptr, int32_t *__restrict__ pos_cnt,
+          int32_t *__restrict__ indices, double *__restrict__ data) {
     for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n_surv;
          q += (unsigned long long)gridDim.x * blockDim.x) {
-        const int2 d = dest[q];
-        if (d.x < 0) continue;
-        const int32_t sy = surv[q].y;
         double a = area[q];
-        const int64_t pos = indptr[d.x] + d.y;
-        const int32_t col = sperm[sy];
-        if (relative) a = a / packed_face_area(spoly + (int64_t)sy * ks, snv[sy]);
-        indices[pos] = col;
+        if (!(a > 0.0)) continue;
+        const int2 r = surv[q];
+        const int64_t row = tperm[r.x] - t_begin;
+        const int slot = atomicSub(pos_cnt + r.x, 1) - 1;
+        const int64_t pos = indptr[row] + slot;
+        if (relative) a = a / packed_face_area(spoly + (int64_t)r.y * ks, snv[r.y]);
+        indices[pos] = sperm[r.y];
         data[pos] = a;
     }
 }
@@ -440,11 +513,8 @@ struct ClipArgs {
     int ks;
     int2 *surv;
     unsigned long long *ctr;
-    const int32_t *tperm;
-    int64_t t_begin;
     double *area;
-    int2 *dest;
-    int32_t *row_cnt;
+    int32_t *pos_cnt;
     cudaEvent_t between;  // recorded between the two kernels (phase timing)
 };
 
@@ -457,14 +527,13 @@ static int launch_clip(const ClipArgs &A, cudaStream_t s) {
                                                      (const double2 *)A.spoly, A.snv, A.ks, A.surv, A.ctr);
     XG_CHECK_LAUNCH();
     if (A.between) XG_CUDA(cudaEventRecord(A.between, s));
-    const size_t smem = sizeof(double2) * 2 * (size_t)(KT + KS) * BT;
+    const size_t smem = sizeof(double2) * 3 * (size_t)(KT + KS) * BT;  // 2 ping-pong lists + 1 staged pair
     auto kern = k_clip_survivors<KT, KS, BT, MINB>;
     XG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem));
     if (per_sm < 1) per_sm = 1;
     kern<<<NUM_SMS * per_sm, BT, smem, s>>>(A.surv, A.ctr, (const double2 *)A.tpoly, A.tnv, A.kt,
-                                            (const double2 *)A.spoly, A.snv, A.ks, A.tperm, A.t_begin,
-                                            A.area, A.dest, A.row_cnt);
+                                            (const double2 *)A.spoly, A.snv, A.ks, A.area, A.pos_cnt);
     XG_CHECK_LAUNCH();
     return XG_OK;
 }
@@ -480,7 +549,7 @@ struct xg_overlap {
     int64_t n_cand = 0, n_surv = 0, nnz = 0;
     cudaStream_t s = nullptr;
     // device buffers
-    DevBuf tperm, tbox, tpoly, tnv, pairs, surv, area, row_cnt, ctr;
+    DevBuf tperm, tbox, tpoly, tnv, pairs, surv, area, pos_cnt, row_cnt, ctr;
     int64_t h_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool stats_valid = false;
     // phase timing: ev[i] is recorded when phase i starts, the last one at the end
@@ -518,7 +587,7 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
     XG_CUDA(job->pairs.alloc(sizeof(int2) * (size_t)cap, s));
     XG_CUDA(job->surv.alloc(sizeof(int2) * (size_t)cap, s));
     XG_CUDA(job->area.alloc(sizeof(double) * (size_t)cap, s));
-    XG_CUDA(cudaMemsetAsync(job->row_cnt.p, 0, sizeof(int32_t) * (size_t)(n_t + 1), s));
+    XG_CUDA(cudaMemsetAsync(job->pos_cnt.p, 0, sizeof(int32_t) * (size_t)(n_t + 1), s));
 
     TraverseParams P;
     P.boxes[0] = source->leaf_box; P.count[0] = source->n_face;
@@ -536,23 +605,28 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
     A.tpoly = job->tpoly.as<double>(); A.tnv = job->tnv.as<uint8_t>(); A.kt = k_t;
     A.spoly = source->poly; A.snv = source->nvert; A.ks = ks;
     A.surv = job->surv.as<int2>(); A.ctr = job->ctr.as<unsigned long long>();
-    A.tperm = job->tperm.as<int32_t>(); A.t_begin = job->t_begin;
-    A.area = job->area.as<double>(); A.row_cnt = job->row_cnt.as<int32_t>();
-    A.dest = job->pairs.as<int2>();  // the candidate arena is dead once k_sat has run
+    A.area = job->area.as<double>(); A.pos_cnt = job->pos_cnt.as<int32_t>();
     if (!job->ev[job->n_ev]) XG_CUDA(cudaEventCreate(&job->ev[job->n_ev]));
     A.between = job->ev[job->n_ev++];  // XG_PHASE_CLIP starts between the two kernels
     int rc;
     // (block size / min-blocks variants 256x2..4, 128x6..8 were measured: 3.30-3.87 ms, 256x3 best)
-    if (k_t == 3 && ks == 3) rc = launch_clip<3, 3, 256, 3>(A, s);
-    else if (k_t == 3 && ks == 4) rc = launch_clip<3, 4, 256, 3>(A, s);
-    else if (k_t == 4 && ks == 3) rc = launch_clip<4, 3, 256, 3>(A, s);
-    else if (k_t == 4 && ks == 4) rc = launch_clip<4, 4, 256, 3>(A, s);
+#ifndef XG_CLIP_BT
+#define XG_CLIP_BT 256
+#define XG_CLIP_MINB 2
+#endif
+    if (k_t == 3 && ks == 3) rc = launch_clip<3, 3, XG_CLIP_BT, XG_CLIP_MINB>(A, s);
+    else if (k_t == 3 && ks == 4) rc = launch_clip<3, 4, 256, 2>(A, s);
+    else if (k_t == 4 && ks == 3) rc = launch_clip<4, 3, 256, 2>(A, s);
+    else if (k_t == 4 && ks == 4) rc = launch_clip<4, 4, 256, 2>(A, s);
     else if (k_t <= 8 && ks <= 8) rc = launch_clip<8, 8, 128, 2>(A, s);
     else if (k_t <= 16 && ks <= 16) rc = launch_clip<16, 16, 64, 1>(A, s);
     else rc = launch_clip<XG_MAX_N_VERTEX, XG_MAX_N_VERTEX, 32, 1>(A, s);
     if (rc) return rc;
 
     XG_CUDA(job->mark());  // XG_PHASE_ROWPTR
+    k_counts_to_rows<<<(unsigned)div_up(n_t, 256), 256, 0, s>>>(job->pos_cnt.as<int32_t>(), job->tperm.as<int32_t>(),
+                                                               job->t_begin, n_t, job->row_cnt.as<int32_t>());
+    XG_CHECK_LAUNCH();
     {
         cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(job->row_cnt.as<int32_t>(), CastI64());
         size_t tb = 0;
@@ -618,6 +692,7 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
         OV_CUDA(job->tpoly.alloc(sizeof(double) * 2 * (size_t)k_t * (size_t)n_t, s));
         OV_CUDA(job->tnv.alloc((size_t)n_t, s));
         OV_CUDA(job->row_cnt.alloc(sizeof(int32_t) * (size_t)(n_t + 1), s));
+        OV_CUDA(job->pos_cnt.alloc(sizeof(int32_t) * (size_t)(n_t + 1), s));
         PackedMesh pm;
         pm.perm = job->tperm.as<int32_t>(); pm.box = job->tbox.as<Box>();
         pm.poly = job->tpoly.as<double>(); pm.nvert = job->tnv.as<uint8_t>();
@@ -654,9 +729,9 @@ extern "C" int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32
         if (!d_indices || !d_area || !d_indptr) { set_error("xg_overlap_finish: NULL output"); delete job; return XG_ERR_INVALID; }
         const xg_index *src = job->src;
         k_scatter<<<NUM_SMS * 8, 256, 0, s>>>(
-            job->surv.as<int2>(), job->area.as<double>(), job->pairs.as<int2>(),
-            (unsigned long long)job->n_surv, src->perm, (const double2 *)src->poly, src->nvert, src->k,
-            relative, d_indptr, d_indices, d_area);
+            job->surv.as<int2>(), job->area.as<double>(), (unsigned long long)job->n_surv,
+            job->tperm.as<int32_t>(), job->t_begin, src->perm, (const double2 *)src->poly, src->nvert,
+            src->k, relative, d_indptr, job->pos_cnt.as<int32_t>(), d_indices, d_area);
         // rows longer than SORT_SHORT are queued in the (now dead) target box buffer
         unsigned long long *n_long = job->ctr.as<unsigned long long>() + CTR_LONG;
         int32_t *long_rows = job->tbox.as<int32_t>();
