@@ -173,7 +173,7 @@ def run_ours(args) -> int:
 
     import xugrid_b200 as xb
     from xugrid_b200 import sparse
-    from xugrid_b200.distributed import all_gather_columns, shard_range, target_range_box
+    from xugrid_b200.distributed import all_gather_columns, shard_range, sharded_upload, target_range_box
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -184,6 +184,8 @@ def run_ours(args) -> int:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     sxy, sf, txy, tf, values = make_workload(args.n_side)
@@ -194,7 +196,6 @@ def run_ours(args) -> int:
          dict(sxy=sxy, sf=sf, txy=txy, tf=tf, values=values).items()}
     h_out = torch.empty((1, n_t), dtype=torch.float64).pin_memory()
     d = {k: v.to(dev) for k, v in h.items()}
-    h2d_bytes = sum(v.numel() * v.element_size() for v in h.values())
     d2h_bytes = h_out.numel() * h_out.element_size()
 
     state = {}
@@ -216,8 +217,17 @@ def run_ours(args) -> int:
     src_grid = xb.Ugrid2d(sxy[:, 0], sxy[:, 1], -1, sf, device=dev)
     tgt_grid = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf, device=dev)
     for g in (src_grid, tgt_grid):
-        g.prefetch()
+        g.prefetch()  # first call: pinned staging copy (int32 connectivity), outside the timed region
     torch.cuda.synchronize()
+    nbytes = lambda t: t.numel() * t.element_size()
+    if world == 1:
+        h2d_bytes = sum(nbytes(t) for t in (src_grid._xy_pin, src_grid._faces_pin, tgt_grid._xy_pin,
+                                            tgt_grid._faces_pin, h["values"]))
+    else:
+        # per rank: 1/world of the replicated arrays (assembled over NVLink) + its own target rows
+        h2d_bytes = (sum(nbytes(t) for t in (src_grid._xy_pin, src_grid._faces_pin, tgt_grid._xy_pin,
+                                             h["values"])) // world
+                     + nbytes(tgt_grid._faces_pin[b:e]))
 
     def e2e_step():
         src_grid.release_device()
@@ -226,8 +236,8 @@ def run_ours(args) -> int:
             r = xb.OverlapRegridder(src_grid, tgt_grid, method="mean")
             state["e2e_out"] = r.regrid(h["values"])  # pinned host tensor in, pinned host tensor out
         else:
-            r = xb.OverlapRegridder(src_grid, tgt_grid, method="mean", target_range=(b, e))
-            local = r.regrid(h["values"].to(dev, non_blocking=True))
+            r = xb.OverlapRegridder(src_grid, tgt_grid, method="mean", target_range=(b, e), sharded_upload=True)
+            local = r.regrid(sharded_upload(h["values"].reshape(-1), dev).reshape(1, -1))
             h_out.copy_(all_gather_columns(local, n_t), non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
@@ -278,14 +288,26 @@ def run_ours(args) -> int:
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         k_t = k_s = 3
-        # dominant kernel k_clip_survivors: per surviving pair it reads the pair ids (8 B) and
-        # both polygons (k*16 B each), writes one area (8 B) and bumps one row counter (4 B)
-        # -- DESIGN.md section 5
-        clip_bytes = stats.clip_pairs * (8 + 16 * k_t + 16 * k_s + 8 + 4)
-        clip_ms = phases.get("clip", float("nan"))
-        achieved = clip_bytes / (clip_ms * 1e-3) / 1e9 if clip_ms and clip_ms > 0 else None
-        # SURVEY 8(d) gather model for the whole build of this rank's rows
         rows = e - b
+        # algorithmic bytes per launch of the three big kernels:
+        #  k_traverse        one 1 KB node (32 boxes x 32 B) per node visit, one 32 B box per target,
+        #                    8 B per candidate pair written
+        #  k_sat             per candidate: pair ids (8 B) + both polygons (k*16 B each); 8 B per survivor written
+        #  k_clip_survivors  per survivor: pair ids (8 B) + both polygons, one area (8 B), one row counter (4 B)
+        kern = {
+            "k_traverse": (stats.node_visits * 1024 + rows * 32 + stats.candidates * 8, phases.get("traverse")),
+            "k_sat<3,3>": (stats.candidates * (8 + 16 * k_t + 16 * k_s) + stats.clip_pairs * 8, phases.get("sat")),
+            "k_clip_survivors<3,3>": (stats.clip_pairs * (8 + 16 * k_t + 16 * k_s + 8 + 4), phases.get("clip")),
+        }
+        kernels = {}
+        for name, (nbytes_k, ms_k) in kern.items():
+            ach = nbytes_k / (ms_k * 1e-3) / 1e9 if ms_k and ms_k > 0 else None
+            kernels[name] = {"algorithmic_bytes": nbytes_k, "ms": ms_k, "achieved": ach,
+                             "frac": (ach / peak) if ach else None}
+        dominant = max(kernels, key=lambda k_: kernels[k_]["ms"] or 0.0)
+        clip_bytes, clip_ms = kernels[dominant]["algorithmic_bytes"], kernels[dominant]["ms"]
+        achieved = kernels[dominant]["achieved"]
+        # SURVEY 8(d) gather model for the whole build of this rank's rows
         # (wide BVH: one node visit = one coalesced load of 32 boxes x 32 B, shared by the 32
         #  targets of a tile, so the per-lane leaf tests C add no memory traffic)
         b_build = (rows * (k_t * 4 + k_t * 16) + stats.node_visits * 32 * 32
@@ -297,7 +319,7 @@ def run_ours(args) -> int:
         if os.path.exists(prof) and world == 1:
             pj = json.load(open(prof))
             if pj.get("n_side") == args.n_side:
-                traffic = pj.get("dram_bytes_per_launch")
+                traffic = pj.get("dram_bytes_per_launch", {}).get(dominant.split("<")[0])
         n_levels = state["tree"].n_levels
         line = {
             "metric": METRIC, "value": n_t / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -311,11 +333,13 @@ def run_ours(args) -> int:
             },
             "e2e": {"value": n_t / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": 6 + n_levels + 8 + 1,
-            "roofline": {"bound": "hbm", "kernel": "k_clip_survivors<3,3>", "achieved": achieved, "peak": peak,
+            "gpu_launches": 6 + n_levels + 9 + 1,
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes": clip_bytes, "ms": clip_ms,
-                         "note": "fp64/issue-bound clipping kernel; see DESIGN.md section 5"},
+                         "note": "dominant = slowest kernel of this run; all three big kernels under "
+                                 "roofline_kernels (instruction-issue bound, see DESIGN.md section 5)"},
+            "roofline_kernels": kernels,
             "roofline_build": {"model": "SURVEY 8(d) gather model", "bytes": b_build, "ms": build_ms,
                                "achieved": b_build / (build_ms * 1e-3) / 1e9 if build_ms else None,
                                "frac": b_build / (build_ms * 1e-3) / 1e9 / peak if build_ms else None,

@@ -58,3 +58,37 @@ def test_two_rank_sharded_regrid_matches_single():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+def _upload_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from xugrid_b200.distributed import sharded_upload
+
+        ok = True
+        for n in (0, 1, 7, 10):  # shorter than, not a multiple of, and a multiple of the world size
+            host = torch.arange(n * 3, dtype=torch.int32).reshape(n, 3)
+            full = sharded_upload(host, torch.device("cpu"))
+            ok = ok and full.shape == host.shape and bool(torch.equal(full, host))
+        xy = torch.from_numpy(np.random.default_rng(5).random((11, 2)))
+        ok = ok and bool(torch.equal(sharded_upload(xy, torch.device("cpu")), xy))
+        q.put(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_upload_replicates_a_host_array():
+    """every rank uploads 1/world of a host array; the all-gather gives all of it to each"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_upload_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True and q.get(timeout=10) is True

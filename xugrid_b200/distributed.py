@@ -65,6 +65,31 @@ def all_gather_columns(local: torch.Tensor, n_total: int, group: Optional[dist.P
     return full
 
 
+def sharded_upload(host: torch.Tensor, device: torch.device,
+                   group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """
+    Replicate a (pinned) host array that every rank holds on every GPU without
+    every rank pulling all of it over its own PCIe link: rank r uploads rows
+    ``shard_range(n, r, world)`` (1/world of the bytes, all links in parallel) and
+    one all_gather_into_tensor over NVLink assembles the full array on each GPU.
+    Falls back to a plain upload outside a process group.  Runs on the current
+    stream.
+    """
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return host.to(device, non_blocking=True)
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = int(host.shape[0])
+    pad = max_shard(n, world)
+    b, e = shard_range(n, rank, world)
+    recv = torch.empty((world * pad,) + tuple(host.shape[1:]), dtype=host.dtype, device=device)
+    send = torch.empty((pad,) + tuple(host.shape[1:]), dtype=host.dtype, device=device)
+    if e > b:
+        send[: e - b].copy_(host[b:e], non_blocking=True)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv[:n]
+
+
 def target_range_box(xy: torch.Tensor, faces: torch.Tensor, begin: int, end: int):
     """(xmin, xmax, ymin, ymax) of the target faces [begin, end) (device tensors);
     the clip box of a shard's source index."""

@@ -69,6 +69,7 @@ class Ugrid2d:
         self._ready = None
         self._xy_ready = None
         self._chunks = None
+        self._face_range = None
 
     # ---- basic properties -------------------------------------------------------
     @property
@@ -106,26 +107,59 @@ class Ugrid2d:
             return torch.device("cuda", torch.cuda.current_device())
         return torch.device(self.device)
 
-    def prefetch(self, n_chunks: int = 1) -> None:
+    def _stage(self) -> None:
+        """Pinned host staging copy, made once per grid.  Connectivity is staged as
+        int32 whenever the node count allows it (the kernels take either width):
+        that halves the bytes every later upload moves over PCIe."""
+        if self._xy_pin is None:
+            self._xy_pin = torch.from_numpy(self.node_coordinates).pin_memory()
+            conn = self.face_node_connectivity
+            if conn.dtype != np.int32 and self.n_node < (1 << 31):
+                conn = conn.astype(np.int32)
+            self._faces_pin = torch.from_numpy(np.ascontiguousarray(conn)).pin_memory()
+
+    def prefetch(self, n_chunks: int = 1, face_range: Optional[Tuple[int, int]] = None,
+                 sharded: bool = False) -> None:
         """Start the host-to-device copy of the mesh on the side (copy) stream.
         The first call pins a host staging copy; later uploads (after
         ``release_device``) are asynchronous DMA transfers that overlap with
         kernels on the compute stream.  With ``n_chunks > 1`` the connectivity
         goes up in contiguous face ranges, each with its own event, so that a
-        consumer can start on the first range while the rest is in flight."""
+        consumer can start on the first range while the rest is in flight.
+        ``face_range=(b, e)``: only that range of the connectivity is uploaded
+        (a rank that owns a range of target faces needs nothing else).
+        ``sharded=True`` (inside an initialised process group whose ranks all
+        hold the same host mesh): every rank uploads 1/world of the arrays over
+        its own PCIe link and the full mesh is assembled with an all-gather over
+        NVLink."""
         if self._xy_d is not None:
             return
         _native.lib()  # raises when there is no GPU: no CPU fallback
         dev = self._dev()
-        if self._xy_pin is None:
-            self._xy_pin = torch.from_numpy(self.node_coordinates).pin_memory()
-            self._faces_pin = torch.from_numpy(self.face_node_connectivity).pin_memory()
+        self._stage()
         copy_stream = _copy_stream(dev)
         n = self.n_face
-        n_chunks = max(1, min(int(n_chunks), n)) if n > 0 else 1
-        bounds = [(n * c) // n_chunks for c in range(n_chunks + 1)]
+        if sharded:
+            from .distributed import sharded_upload
+        if sharded and face_range is None:
+            with torch.cuda.stream(copy_stream):
+                self._xy_d = sharded_upload(self._xy_pin, dev)
+                self._faces_d = sharded_upload(self._faces_pin, dev)
+                self._xy_ready = torch.cuda.Event()
+                self._xy_ready.record(copy_stream)
+                self._chunks = [(0, n, self._xy_ready)]
+                self._ready = self._xy_ready
+                self._face_range = None
+            return
+        fb, fe = (0, n) if face_range is None else (max(0, int(face_range[0])), min(n, int(face_range[1])))
+        m = max(0, fe - fb)
+        n_chunks = max(1, min(int(n_chunks), m)) if m > 0 else 1
+        bounds = [fb + (m * c) // n_chunks for c in range(n_chunks + 1)]
         with torch.cuda.stream(copy_stream):
-            self._xy_d = self._xy_pin.to(dev, non_blocking=True)
+            if sharded:
+                self._xy_d = sharded_upload(self._xy_pin, dev)
+            else:
+                self._xy_d = self._xy_pin.to(dev, non_blocking=True)
             self._xy_ready = torch.cuda.Event()
             self._xy_ready.record(copy_stream)
             self._faces_d = torch.empty(self._faces_pin.shape, dtype=self._faces_pin.dtype, device=dev)
@@ -136,15 +170,38 @@ class Ugrid2d:
                 ev.record(copy_stream)
                 self._chunks.append((b, e, ev))
             self._ready = self._chunks[-1][2] if self._chunks else self._xy_ready
+            self._face_range = None if (fb, fe) == (0, n) else (fb, fe)
+
+    def _complete_upload(self) -> None:
+        """After a range-limited prefetch: bring up the rest of the connectivity."""
+        if self._face_range is None:
+            return
+        fb, fe = self._face_range
+        copy_stream = _copy_stream(self._dev())
+        with torch.cuda.stream(copy_stream):
+            if fb > 0:
+                self._faces_d[:fb].copy_(self._faces_pin[:fb], non_blocking=True)
+            if fe < self.n_face:
+                self._faces_d[fe:].copy_(self._faces_pin[fe:], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        torch.cuda.current_stream(self._xy_d.device).wait_event(ev)
+        self._face_range = None
 
     def _adopt(self, cur) -> None:
         # tensors were allocated on the copy stream: tell the allocator who uses them
         self._xy_d.record_stream(cur)
         self._faces_d.record_stream(cur)
 
-    def device_arrays(self) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(n_node, 2) float64 and (n_face, k) int tensors in HBM (cached)."""
+    def device_arrays(self, face_range: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(n_node, 2) float64 and (n_face, k) int tensors in HBM (cached).  With
+        ``face_range`` the caller promises to touch only those rows of the
+        connectivity (the rest may not have been uploaded)."""
         self.prefetch()
+        if self._face_range is not None and (
+            face_range is None or face_range[0] < self._face_range[0] or face_range[1] > self._face_range[1]
+        ):
+            self._complete_upload()
         if self._ready is not None:
             cur = torch.cuda.current_stream(self._xy_d.device)
             cur.wait_event(self._ready)
@@ -158,7 +215,7 @@ class Ugrid2d:
         for the coordinates; call ``wait_chunk(i)`` before using face range i.
         None when the mesh is already fully resident."""
         self.prefetch()
-        if self._ready is None or not self._chunks or len(self._chunks) < 2:
+        if self._ready is None or not self._chunks or len(self._chunks) < 2 or self._face_range is not None:
             return None
         cur = torch.cuda.current_stream(self._xy_d.device)
         cur.wait_event(self._xy_ready)
@@ -180,6 +237,7 @@ class Ugrid2d:
         self._ready = None
         self._xy_ready = None
         self._chunks = None
+        self._face_range = None
 
     @property
     def celltree(self) -> CellTree2d:

@@ -107,12 +107,14 @@ class UnstructuredGrid2d:
     def overlap(self, other: "UnstructuredGrid2d", relative: bool,
                 target_range: Optional[Tuple[int, int]] = None) -> MatrixCSR:
         """unstructured.py:109-135 + sparse.py:119-127, as one device CSR."""
+        # the source index first: its build must not wait for target arrays that are
+        # queued behind the source on the copy stream
+        tree = self.ugrid_topology.celltree if target_range is None else None
         chunks = other.ugrid_topology.device_chunks() if target_range is None else None
         if chunks is not None:
             # the target connectivity is still arriving in face ranges: overlap the
             # weights of range c with the transfer of range c + 1
             xy, faces, ranges = chunks
-            tree = self.ugrid_topology.celltree
             self.last_tree = tree
             parts, offset = [], 0
             for c, (b, e) in enumerate(ranges):
@@ -124,8 +126,8 @@ class UnstructuredGrid2d:
             indices = torch.cat([p[1] for p in parts])
             data = torch.cat([p[2] for p in parts])
             return MatrixCSR(data, indices, indptr, other.size, self.size, int(data.numel()))
-        xy, faces = other.ugrid_topology.device_arrays()
         t_begin, t_end = (0, other.size) if target_range is None else target_range
+        xy, faces = other.ugrid_topology.device_arrays(face_range=(t_begin, t_end))
         if target_range is not None and (t_end - t_begin) < other.size and t_end > t_begin:
             # a shard: index only the source faces its targets can touch
             from .celltree import CellTree2d
@@ -134,7 +136,7 @@ class UnstructuredGrid2d:
             sxy, sfaces = self.ugrid_topology.device_arrays()
             tree = CellTree2d(sxy, sfaces, -1, device=sxy.device,
                               clip_box=target_range_box(xy, faces, t_begin, t_end))
-        else:
+        elif tree is None:
             tree = self.ugrid_topology.celltree
         self.last_tree = tree
         indptr, indices, data = tree.intersect_faces_csr(
@@ -256,16 +258,27 @@ class BaseRegridder(abc.ABC):
     _TARGET_CHUNKS = 4  # face ranges a large target mesh is uploaded in
 
     def __init__(self, source, target, tolerance: Optional[float] = None,
-                 target_range: Optional[Tuple[int, int]] = None):
+                 target_range: Optional[Tuple[int, int]] = None, sharded_upload: bool = False):
+        """``target_range=(b, e)``: this process owns only those target faces (one
+        process per GPU, see distributed.py).  ``sharded_upload=True`` (all ranks of
+        the default process group hold the same host meshes): the source mesh and the
+        target coordinates go up 1/world per rank and are replicated over NVLink."""
         self._source = setup_grid(source)
         self._target = setup_grid(target)
         self._weights = None
         self._target_range = target_range
         # start both uploads on the copy stream: the index build over the source
         # overlaps with the transfer of the target
-        self._source.to_unstructured().ugrid_topology.prefetch()
+        src_grid = self._source.to_unstructured().ugrid_topology
         tgt_grid = self._target.to_unstructured().ugrid_topology
-        tgt_grid.prefetch(n_chunks=self._TARGET_CHUNKS if tgt_grid.n_face >= (1 << 20) else 1)
+        if target_range is None:
+            src_grid.prefetch(sharded=sharded_upload)
+            tgt_grid.prefetch(n_chunks=self._TARGET_CHUNKS if tgt_grid.n_face >= (1 << 20) else 1)
+        else:
+            # a shard: its (small) target range first, so that the clip box of the
+            # source index is known while the source mesh is still arriving
+            tgt_grid.prefetch(face_range=target_range, sharded=sharded_upload)
+            src_grid.prefetch(sharded=sharded_upload)
         self._compute_weights(self._source, self._target, tolerance)
 
     # ---- method selection (regridder.py:124-141) --------------------------------------
@@ -442,8 +455,9 @@ class OverlapRegridder(BaseOverlapRegridder):
     _METHODS = ABSOLUTE_OVERLAP_METHODS
 
     def __init__(self, source, target, method: Union[str, Callable] = "mean",
-                 target_range: Optional[Tuple[int, int]] = None):
-        super().__init__(source=source, target=target, target_range=target_range)
+                 target_range: Optional[Tuple[int, int]] = None, sharded_upload: bool = False):
+        super().__init__(source=source, target=target, target_range=target_range,
+                         sharded_upload=sharded_upload)
         self._setup_regrid(method)
 
     def _compute_weights(self, source, target, tolerance=None) -> None:
@@ -466,8 +480,9 @@ class RelativeOverlapRegridder(BaseOverlapRegridder):
     _METHODS = RELATIVE_OVERLAP_METHODS
 
     def __init__(self, source, target, method: Union[str, Callable] = "first_order_conservative",
-                 target_range: Optional[Tuple[int, int]] = None):
-        super().__init__(source=source, target=target, tolerance=None, target_range=target_range)
+                 target_range: Optional[Tuple[int, int]] = None, sharded_upload: bool = False):
+        super().__init__(source=source, target=target, tolerance=None, target_range=target_range,
+                         sharded_upload=sharded_upload)
         self._setup_regrid(method)
 
     def _compute_weights(self, source, target, tolerance=None) -> None:
