@@ -38,7 +38,7 @@ namespace xg {
 constexpr int TRAV_WARPS = 8;
 constexpr int TRAV_STACK = 256;
 constexpr int TRAV_QCAP = 128;    // pair queue entries per warp
-constexpr int TRAV_QFLUSH = 96;   // flush threshold (a child test adds <= 32)
+constexpr int TRAV_QFLUSH = 64;   // flush threshold (one trip tests two children: adds <= 64)
 constexpr int PAIRS_PER_TARGET_GUESS = 16;
 
 // device counters of one job
@@ -51,8 +51,10 @@ struct TraverseParams {
 };
 
 __device__ __forceinline__ bool boxes_intersect(const Box &a, const Box &b) {
-    // strict: touching boxes do not intersect
-    return a.xmin < b.xmax && b.xmin < a.xmax && a.ymin < b.ymax && b.ymin < a.ymax;
+    // strict: touching boxes do not intersect.  Bitwise &: all four compares are
+    // evaluated (a short-circuit makes the second half of a shared-memory box load
+    // wait for the compare on the first half)
+    return (a.xmin < b.xmax) & (b.xmin < a.xmax) & (a.ymin < b.ymax) & (b.ymin < a.ymax);
 }
 
 // 16-byte asynchronous copy global -> shared (LDGSTS); completion is awaited with
@@ -139,14 +141,23 @@ k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t,
             }
         } else {
             tests += __popc(m);
+            // two children per trip: both boxes are loaded before either is tested
             while (m) {
-                const int c = __ffs(m) - 1;
+                const int ca = __ffs(m) - 1;
                 m &= m - 1;
-                const Box b = s_node[w][c];
-                const bool hit = boxes_intersect(tb, b);
-                const unsigned hm = __ballot_sync(0xffffffffu, hit);
-                if (hit) s_q[w][qn + __popc(hm & lt_mask)] = make_int2((int32_t)t, (int32_t)(c0 + c));
-                qn += __popc(hm);
+                const bool two = m != 0u;
+                const int cb2 = two ? __ffs(m) - 1 : ca;
+                m &= m - 1;
+                const Box ba = s_node[w][ca];
+                const Box bb = s_node[w][cb2];
+                const bool hita = boxes_intersect(tb, ba);
+                const bool hitb = two & boxes_intersect(tb, bb);
+                const unsigned ha = __ballot_sync(0xffffffffu, hita);
+                const unsigned hb = __ballot_sync(0xffffffffu, hitb);
+                const int na = __popc(ha);
+                if (hita) s_q[w][qn + __popc(ha & lt_mask)] = make_int2((int32_t)t, (int32_t)(c0 + ca));
+                if (hitb) s_q[w][qn + na + __popc(hb & lt_mask)] = make_int2((int32_t)t, (int32_t)(c0 + cb2));
+                qn += na + __popc(hb);
                 if (qn >= TRAV_QFLUSH) flush();
             }
         }
