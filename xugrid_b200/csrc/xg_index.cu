@@ -229,10 +229,18 @@ k_face_keys(const double2 *__restrict__ xy, const I *__restrict__ faces, int64_t
         }
     }
     if (diag2_max) {
+        // block-wide max first: one global atomic per block (one per warp on a single
+        // address serialised the kernel: 0.27 ms vs 0.13 ms without the reduction)
+        __shared__ double s_d2[8];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
-        if ((threadIdx.x & 31) == 0 && d2 > 0.0)
-            atomicMax(diag2_max, (unsigned long long)__double_as_longlong(d2));
+        if ((threadIdx.x & 31) == 0) s_d2[threadIdx.x >> 5] = d2;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 1; i < 8; ++i) d2 = fmax(d2, s_d2[i]);
+            if (d2 > 0.0) atomicMax(diag2_max, (unsigned long long)__double_as_longlong(d2));
+        }
     }
 }
 
@@ -442,14 +450,20 @@ int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_
         out->n = n_pack;
     }
     if (n_pack > 0) {
+        // only the leading Morton bits that can separate n faces are sorted (8-bit radix
+        // digits: 10 M faces -> 24 bits -> 3 passes instead of 4); faces that share those
+        // bits keep their input order (the sort is stable)
+        int bits = 16;
+        while (bits < 32 && ((int64_t)1 << bits) < n_pack) bits += 8;
+        const int begin_bit = 32 - bits;
         size_t tb = 0;
         XG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in.as<uint32_t>(),
                                                 keys_out.as<uint32_t>(), ids_in.as<int32_t>(),
-                                                out->perm, n_pack, 0, 32, s));
+                                                out->perm, n_pack, begin_bit, 32, s));
         XG_CUDA(tmp.alloc(tb, s));
         XG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys_in.as<uint32_t>(),
                                                 keys_out.as<uint32_t>(), ids_in.as<int32_t>(),
-                                                out->perm, n_pack, 0, 32, s));
+                                                out->perm, n_pack, begin_bit, 32, s));
     }
     if (idx_bytes == 4)
         rc = launch_pack<int32_t>(xy, (const int32_t *)d_faces, k, out->perm, n_pack, out->box,

@@ -17,10 +17,12 @@
 //   k_sat                one thread per candidate pair: separating-axis filter;
 //                        survivors appended to a dense list
 //   k_clip_survivors     one thread per survivor: Sutherland-Hodgman area,
-//                        warp-uniform code; positive areas bump their row count
+//                        warp-uniform code; a positive area is written straight
+//                        into the target's provisional row (rows in sorted target
+//                        order, sized by the candidate counts of the walk)
 //   cub ExclusiveSum     CSR row pointer in the caller's row order
-//   k_scatter + k_sort_rows (xg_overlap_finish)  entries dropped into their
-//                        rows, every row ordered by ascending source index
+//   k_move_rows (xg_overlap_finish)  provisional row -> caller's row, entries
+//                        ordered by ascending source index on the way
 // The arena is sized from a density guess (16 candidates per target); if the
 // walk finds more, the job is re-run once with the exact size the first walk
 // counted (the reference always walks twice: count pass + fill pass).
@@ -37,8 +39,12 @@ namespace xg {
 
 constexpr int TRAV_WARPS = 8;
 constexpr int TRAV_STACK = 256;
-constexpr int TRAV_QCAP = 128;    // pair queue entries per warp
-constexpr int TRAV_QFLUSH = 64;   // flush threshold (one trip tests two children: adds <= 64)
+#ifndef XG_TRAV_U
+#define XG_TRAV_U 3
+#endif
+constexpr int TRAV_U = XG_TRAV_U;               // children tested per leaf trip
+constexpr int TRAV_QFLUSH = 64;                 // flush threshold
+constexpr int TRAV_QCAP = TRAV_QFLUSH + 32 * TRAV_U;  // pair queue entries per warp (one trip adds <= 32 * TRAV_U)
 constexpr int PAIRS_PER_TARGET_GUESS = 16;
 
 // device counters of one job
@@ -72,12 +78,18 @@ __device__ __forceinline__ int2 ld_int2_here(const int2 *p) {
     asm volatile("ld.global.nc.v2.s32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
+__device__ __forceinline__ int64_t ld_i64_here(const int64_t *p) {
+    long long v;
+    asm volatile("ld.global.nc.s64 %0, [%1];\n" : "=l"(v) : "l"(p));
+    return (int64_t)v;
+}
 __device__ __forceinline__ void schedule_fence() { asm volatile("" ::: "memory"); }
 
 // pairs[i] = {sorted target position, sorted source position}
 __global__ void __launch_bounds__(TRAV_WARPS * 32)
 k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t,
-           int2 *__restrict__ pairs, unsigned long long cap, unsigned long long *__restrict__ ctr) {
+           int2 *__restrict__ pairs, unsigned long long cap, int32_t *__restrict__ cand_cnt,
+           unsigned long long *__restrict__ ctr) {
     __shared__ Box s_node[TRAV_WARPS][32];
     __shared__ int32_t s_stack[TRAV_WARPS][TRAV_STACK];
     __shared__ int2 s_q[TRAV_WARPS][TRAV_QCAP];
@@ -101,6 +113,7 @@ k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t,
     int sp = 1, qn = 0;
     if (lane == 0) s_stack[w][0] = P.top << 27;
     unsigned visits = 0, tests = 0;
+    int my_cand = 0;  // candidates of this lane's target = capacity of its provisional row
 
     auto flush = [&]() {
         __syncwarp();
@@ -141,29 +154,39 @@ k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t,
             }
         } else {
             tests += __popc(m);
-            // two children per trip: both boxes are loaded before either is tested
+            // TRAV_U children per trip: all boxes are loaded before any is tested
             while (m) {
-                const int ca = __ffs(m) - 1;
-                m &= m - 1;
-                const bool two = m != 0u;
-                const int cb2 = two ? __ffs(m) - 1 : ca;
-                m &= m - 1;
-                const Box ba = s_node[w][ca];
-                const Box bb = s_node[w][cb2];
-                const bool hita = boxes_intersect(tb, ba);
-                const bool hitb = two & boxes_intersect(tb, bb);
-                const unsigned ha = __ballot_sync(0xffffffffu, hita);
-                const unsigned hb = __ballot_sync(0xffffffffu, hitb);
-                const int na = __popc(ha);
-                if (hita) s_q[w][qn + __popc(ha & lt_mask)] = make_int2((int32_t)t, (int32_t)(c0 + ca));
-                if (hitb) s_q[w][qn + na + __popc(hb & lt_mask)] = make_int2((int32_t)t, (int32_t)(c0 + cb2));
-                qn += na + __popc(hb);
+                int c[TRAV_U];
+                bool on[TRAV_U];
+#pragma unroll
+                for (int u = 0; u < TRAV_U; ++u) {
+                    on[u] = m != 0u;
+                    c[u] = on[u] ? __ffs(m) - 1 : 0;
+                    m &= m - 1;
+                }
+                Box bx[TRAV_U];
+#pragma unroll
+                for (int u = 0; u < TRAV_U; ++u) bx[u] = s_node[w][c[u]];
+                unsigned hm[TRAV_U];
+                bool hit[TRAV_U];
+#pragma unroll
+                for (int u = 0; u < TRAV_U; ++u) {
+                    hit[u] = on[u] & boxes_intersect(tb, bx[u]);
+                    hm[u] = __ballot_sync(0xffffffffu, hit[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < TRAV_U; ++u) {
+                    if (hit[u]) s_q[w][qn + __popc(hm[u] & lt_mask)] = make_int2((int32_t)t, (int32_t)(c0 + c[u]));
+                    my_cand += hit[u] ? 1 : 0;
+                    qn += __popc(hm[u]);
+                }
                 if (qn >= TRAV_QFLUSH) flush();
             }
         }
         __syncwarp();
     }
     if (qn > 0) flush();
+    if (valid) cand_cnt[t] = my_cand;
     if (lane == 0) {
         atomicAdd(ctr + CTR_VISITS, (unsigned long long)visits);
         atomicAdd(ctr + CTR_TESTS, (unsigned long long)tests * 32ull);
@@ -314,12 +337,19 @@ k_sat(const int2 *__restrict__ pairs, unsigned long long cap, const double2 *__r
 // into its shared-memory slots with cp.async while the current one is clipped,
 // and the survivor record after that is already in flight to a register.
 // Shared memory per thread: two (KT+KS)-vertex ping-pong lists + one staged pair.
+//
+// A positive area goes straight into the target's PROVISIONAL row (rows in sorted
+// target order, capacity = candidates counted by the walk): slot = atomicAdd on the
+// row's fill counter.  The atomic's return value is only needed one trip later
+// (pend_*), and it is issued after the cp.async wait of that next trip so that it
+// cannot delay the wait (both end up on the same hardware scoreboard).
 template <int KT, int KS, int BT, int MINB>
 __global__ void __launch_bounds__(BT, MINB)
 k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__restrict__ ctr,
                  const double2 *__restrict__ tpoly, const uint8_t *__restrict__ tnv, int kt,
                  const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks,
-                 double *__restrict__ area, int32_t *__restrict__ pos_cnt) {
+                 const int64_t *__restrict__ prov_ptr, int32_t *__restrict__ fill_cnt,
+                 int32_t *__restrict__ prov_col, double *__restrict__ prov_val) {
     extern __shared__ double2 s_buf[];
     constexpr int M = KT + KS;
     const unsigned long long n_surv = ctr[CTR_SURV];
@@ -340,30 +370,39 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
             if (j < ks) cp_async16(stg + (KT + j) * BT, sp + j);
     };
 
-    // loop-carried pipeline registers: r / na / nb describe the STAGED survivor,
-    // r_next the one after it
+    // loop-carried pipeline registers: r / na / nb / base describe the STAGED
+    // survivor, r_next the one after it; pend_* the clipped one awaiting its slot
     int2 r = make_int2(0, 0), r_next = make_int2(0, 0);
+    int64_t base = 0;    // prov_ptr of the staged survivor's target
     int na = 3, nb = 3;  // vertex counts (looked up for K > 3 only)
     if (q < n_surv) {
         r = surv[q];
         stage(r);
+        base = prov_ptr[r.x];
         if (KT > 3) na = tnv[r.x] & 0x7f;
         if (KS > 3) nb = snv[r.y] & 0x7f;
     }
     if (q + stride < n_surv) r_next = surv[q + stride];
+    int2 pend_r = make_int2(-1, 0);  // x < 0: nothing pending
+    int64_t pend_base = 0;
+    double pend_ar = 0.0;
     for (; q < n_surv; q += stride) {
         cp_async_wait_all();
+        int32_t slot = 0;
+        if (pend_r.x >= 0) slot = atomicAdd(fill_cnt + pend_r.x, 1);
         double2 a[KT], b[KS];
 #pragma unroll
         for (int j = 0; j < KT; ++j) a[j] = stg[j * BT];
 #pragma unroll
         for (int j = 0; j < KS; ++j) b[j] = stg[(KT + j) * BT];
         const int2 r_cur = r;
+        const int64_t base_cur = base;
         const int na_cur = na, nb_cur = nb;
         // ---- prefetch
         if (q + stride < n_surv) {
             r = r_next;
             stage(r);
+            base = ld_i64_here(prov_ptr + r.x);
             if (KT > 3) na = tnv[r.x] & 0x7f;
             if (KS > 3) nb = snv[r.y] & 0x7f;
         }
@@ -384,10 +423,19 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
         } else {
             ar = clip_area<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT);
         }
-        if (!(ar > 0.0)) ar = 0.0;
-        area[q] = ar;
-        // entries per target, counted by SORTED target position (fire-and-forget)
-        if (ar > 0.0) atomicAdd(pos_cnt + r_cur.x, 1);
+        schedule_fence();  // keeps the stores of the pending entry late
+        if (pend_r.x >= 0) {
+            prov_col[pend_base + slot] = pend_r.y;
+            prov_val[pend_base + slot] = pend_ar;
+        }
+        pend_r = (ar > 0.0) ? r_cur : make_int2(-1, 0);
+        pend_base = base_cur;
+        pend_ar = ar;
+    }
+    if (pend_r.x >= 0) {
+        const int32_t slot = atomicAdd(fill_cnt + pend_r.x, 1);
+        prov_col[pend_base + slot] = pend_r.y;
+        prov_val[pend_base + slot] = pend_ar;
     }
 }
 
@@ -410,35 +458,13 @@ __device__ __forceinline__ double packed_face_area(const double2 *__restrict__ p
 }
 
 // rows are counted by sorted target position; the row pointer is in the caller's
-// row order: cnt_row[tperm[t] - t_begin] = pos_cnt[t]
+// row order: cnt_row[tperm[t] - t_begin] = fill_cnt[t]
 __global__ void __launch_bounds__(256)
-k_counts_to_rows(const int32_t *__restrict__ pos_cnt, const int32_t *__restrict__ tperm, int64_t t_begin,
+k_counts_to_rows(const int32_t *__restrict__ fill_cnt, const int32_t *__restrict__ tperm, int64_t t_begin,
                  int64_t n_t, int32_t *__restrict__ cnt_row) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t < n_t) cnt_row[tperm[t] - t_begin] = pos_cnt[t];
+    if (t < n_t) cnt_row[tperm[t] - t_begin] = fill_cnt[t];
     if (t == 0) cnt_row[n_t] = 0;
-}
-
-// one thread per survivor: a positive area takes the next free slot of its row
-// (pos_cnt counts down, so the row fills from the back; k_sort_rows orders it)
-__global__ void __launch_bounds__(256)
-k_scatter(const int2 *__restrict__ surv, const double *__restrict__ area, unsigned long long n_surv,
-          const int32_t *__restrict__ tperm, int64_t t_begin, const int32_t *__restrict__ sperm,
-          const double2 *__restrict__ spoly, const uint8_t *__restrict__ snv, int ks, int relative,
-          const int64_t *__restrict__ indptr, int32_t *__restrict__ pos_cnt,
-          int32_t *__restrict__ indices, double *__restrict__ data) {
-    for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n_surv;
-         q += (unsigned long long)gridDim.x * blockDim.x) {
-        double a = area[q];
-        if (!(a > 0.0)) continue;
-        const int2 r = surv[q];
-        const int64_t row = tperm[r.x] - t_begin;
-        const int slot = atomicSub(pos_cnt + r.x, 1) - 1;
-        const int64_t pos = indptr[row] + slot;
-        if (relative) a = a / packed_face_area(spoly + (int64_t)r.y * ks, snv[r.y]);
-        indices[pos] = sperm[r.y];
-        data[pos] = a;
-    }
 }
 
 __device__ __forceinline__ void cswap(int32_t &ka, double &va, int32_t &kb, double &vb) {
@@ -473,42 +499,71 @@ __device__ __forceinline__ void sort_network(int32_t (&k)[16], double (&v)[16]) 
 }
 #undef XG_CS
 
+// what a row needs to go from the provisional CSR to the caller's CSR
+struct RowMove {
+    const int64_t *prov_ptr;   // (n_t + 1) provisional row starts, sorted target order
+    const int32_t *fill_cnt;   // (n_t) entries per provisional row
+    const int32_t *prov_col;   // SORTED source position per entry
+    const double *prov_val;    // overlap area per entry
+    const int32_t *tperm;      // sorted target position -> caller's target face
+    int64_t t_begin;
+    const int32_t *sperm;      // sorted source position -> caller's source face
+    const double2 *spoly;      // packed source polygons (relative weights)
+    const uint8_t *snv;
+    int ks;
+    int relative;
+    const int64_t *indptr;     // caller's row pointer
+    int32_t *indices;
+    double *data;
+};
+
+__device__ __forceinline__ double entry_value(const RowMove &R, int32_t s, double a) {
+    // relative weights: unstructured.py:133-134, area of the source face as connectivity.area computes it
+    return R.relative ? a / packed_face_area(R.spoly + (int64_t)s * R.ks, R.snv[s]) : a;
+}
+
 template <int N>
-__device__ __forceinline__ void sort_row_regs(int64_t b, int n, int32_t *__restrict__ indices,
-                                              double *__restrict__ data) {
+__device__ __forceinline__ void move_row_regs(const RowMove &R, int64_t src, int64_t dst, int n) {
     int32_t k[N];
     double v[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        k[i] = i < n ? indices[b + i] : 0x7fffffff;
-        v[i] = i < n ? data[b + i] : 0.0;
+        k[i] = 0x7fffffff;
+        v[i] = 0.0;
+        if (i < n) {
+            const int32_t s = R.prov_col[src + i];
+            k[i] = R.sperm[s];
+            v[i] = entry_value(R, s, R.prov_val[src + i]);
+        }
     }
     sort_network(k, v);
 #pragma unroll
     for (int i = 0; i < N; ++i)
         if (i < n) {
-            indices[b + i] = k[i];
-            data[b + i] = v[i];
+            R.indices[dst + i] = k[i];
+            R.data[dst + i] = v[i];
         }
 }
 
-constexpr int SORT_SHORT = 16;     // rows up to this length are sorted by one thread in registers
+constexpr int SORT_SHORT = 16;       // rows up to this length are sorted by one thread in registers
 constexpr int SORT_LONG_CAP = 1024;  // rows up to this length are rank-sorted by one warp in shared memory
 
-// one thread per row: ascending source index.  Short rows (the common case at
-// comparable resolutions) go through a fixed network in registers, warp-uniformly
-// (8 or 16 slots by the longest row of the warp); longer rows are queued for
-// k_sort_long_rows.
+// One thread per sorted target: its provisional row -> its row of the caller's
+// CSR, entries in ascending source index (MatrixCSR rows as sparse.py:61-78 would
+// hold them after a stable sort by column).  Consecutive threads read consecutive
+// provisional rows; short rows (the common case at comparable resolutions) go
+// through a fixed network in registers, warp-uniformly (8 or 16 slots by the
+// longest row of the warp); longer rows are queued for k_move_long_rows.
 __global__ void __launch_bounds__(256)
-k_sort_rows(const int64_t *__restrict__ indptr, int64_t n_rows, int32_t *__restrict__ indices,
-            double *__restrict__ data, int32_t *__restrict__ long_rows,
+k_move_rows(const RowMove R, int64_t n_t, int32_t *__restrict__ long_rows,
             unsigned long long *__restrict__ n_long) {
-    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    int64_t b = 0;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t src = 0, dst = 0;
     int n = 0;
-    if (row < n_rows) {
-        b = indptr[row];
-        n = (int)min((int64_t)0x7fffffff, indptr[row + 1] - b);
+    if (t < n_t) {
+        n = R.fill_cnt[t];
+        src = R.prov_ptr[t];
+        dst = R.indptr[R.tperm[t] - R.t_begin];
     }
     const bool is_long = n > SORT_SHORT;
     const unsigned lm = __ballot_sync(0xffffffffu, is_long);
@@ -517,60 +572,70 @@ k_sort_rows(const int64_t *__restrict__ indptr, int64_t n_rows, int32_t *__restr
         unsigned long long base = 0;
         if (lane == __ffs(lm) - 1) base = atomicAdd(n_long, (unsigned long long)__popc(lm));
         base = __shfl_sync(0xffffffffu, base, __ffs(lm) - 1);
-        if (is_long) long_rows[base + __popc(lm & ((1u << lane) - 1u))] = (int32_t)row;
+        if (is_long) long_rows[base + __popc(lm & ((1u << lane) - 1u))] = (int32_t)t;
     }
     const int ns = is_long ? 0 : n;
     const bool wide = __any_sync(0xffffffffu, ns > 8);
     if (wide) {
-        if (ns >= 2) sort_row_regs<16>(b, ns, indices, data);
+        if (ns >= 1) move_row_regs<16>(R, src, dst, ns);
     } else {
-        if (ns >= 2) sort_row_regs<8>(b, ns, indices, data);
+        if (ns >= 1) move_row_regs<8>(R, src, dst, ns);
     }
 }
 
 // one warp per queued row: rank sort through shared memory (source indices of a
 // row are distinct, so the rank of a key is its final position)
 __global__ void __launch_bounds__(128)
-k_sort_long_rows(const int64_t *__restrict__ indptr, const int32_t *__restrict__ long_rows,
-                 const unsigned long long *__restrict__ n_long, int32_t *__restrict__ indices,
-                 double *__restrict__ data) {
+k_move_long_rows(const RowMove R, const int32_t *__restrict__ long_rows,
+                 const unsigned long long *__restrict__ n_long) {
     __shared__ int32_t s_key[4][SORT_LONG_CAP];
     __shared__ double s_val[4][SORT_LONG_CAP];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned long long total = *n_long;
-    for (unsigned long long r = (unsigned long long)blockIdx.x * 4 + w; r < total;
-         r += (unsigned long long)gridDim.x * 4) {
-        const int64_t row = long_rows[r];
-        const int64_t b = indptr[row];
-        const int64_t n = indptr[row + 1] - b;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * 4 + w; q < total;
+         q += (unsigned long long)gridDim.x * 4) {
+        const int64_t t = long_rows[q];
+        const int64_t n = R.fill_cnt[t];
+        const int64_t src = R.prov_ptr[t];
+        const int64_t dst = R.indptr[R.tperm[t] - R.t_begin];
         if (n <= SORT_LONG_CAP) {
             for (int i = lane; i < n; i += 32) {
-                s_key[w][i] = indices[b + i];
-                s_val[w][i] = data[b + i];
+                const int32_t s = R.prov_col[src + i];
+                s_key[w][i] = R.sperm[s];
+                s_val[w][i] = entry_value(R, s, R.prov_val[src + i]);
             }
             __syncwarp();
             for (int i = lane; i < n; i += 32) {
                 const int32_t key = s_key[w][i];
                 int rank = 0;
                 for (int j = 0; j < (int)n; ++j) rank += s_key[w][j] < key ? 1 : 0;
-                indices[b + rank] = key;
-                data[b + rank] = s_val[w][i];
+                R.indices[dst + rank] = key;
+                R.data[dst + rank] = s_val[w][i];
             }
             __syncwarp();
-        } else if (lane == 0) {
-            // beyond any mesh pair seen in practice: in-place insertion sort
-            for (int64_t i = 1; i < n; ++i) {
-                const int32_t key = indices[b + i];
-                const double val = data[b + i];
-                int64_t j = i - 1;
-                while (j >= 0 && indices[b + j] > key) {
-                    indices[b + j + 1] = indices[b + j];
-                    data[b + j + 1] = data[b + j];
-                    --j;
-                }
-                indices[b + j + 1] = key;
-                data[b + j + 1] = val;
+        } else {
+            // beyond any mesh pair seen in practice: copy, then in-place insertion sort by one lane
+            for (int64_t i = lane; i < n; i += 32) {
+                const int32_t s = R.prov_col[src + i];
+                R.indices[dst + i] = R.sperm[s];
+                R.data[dst + i] = entry_value(R, s, R.prov_val[src + i]);
             }
+            __syncwarp();
+            if (lane == 0) {
+                for (int64_t i = 1; i < n; ++i) {
+                    const int32_t key = R.indices[dst + i];
+                    const double val = R.data[dst + i];
+                    int64_t j = i - 1;
+                    while (j >= 0 && R.indices[dst + j] > key) {
+                        R.indices[dst + j + 1] = R.indices[dst + j];
+                        R.data[dst + j + 1] = R.data[dst + j];
+                        --j;
+                    }
+                    R.indices[dst + j + 1] = key;
+                    R.data[dst + j + 1] = val;
+                }
+            }
+            __syncwarp();
         }
     }
 }
@@ -590,9 +655,11 @@ struct ClipArgs {
     int ks;
     int2 *surv;
     unsigned long long *ctr;
-    double *area;
-    int32_t *pos_cnt;
-    cudaEvent_t between;  // recorded between the two kernels (phase timing)
+    int64_t *prov_ptr;   // (n_t + 1) provisional row starts: exclusive scan of the candidate counts
+    int32_t *fill_cnt;   // (n_t + 1) positive areas per sorted target
+    int32_t *prov_col;
+    double *prov_val;
+    cudaEvent_t between;  // recorded before the clip kernel (phase timing)
 };
 
 template <int KT, int KS, int BT, int MINB>
@@ -611,7 +678,8 @@ static int launch_clip(const ClipArgs &A, cudaStream_t s) {
     XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem));
     if (per_sm < 1) per_sm = 1;
     kern<<<NUM_SMS * per_sm, BT, smem, s>>>(A.surv, A.ctr, (const double2 *)A.tpoly, A.tnv, A.kt,
-                                            (const double2 *)A.spoly, A.snv, A.ks, A.area, A.pos_cnt);
+                                            (const double2 *)A.spoly, A.snv, A.ks, A.prov_ptr, A.fill_cnt, A.prov_col,
+                                            A.prov_val);
     XG_CHECK_LAUNCH();
     return XG_OK;
 }
@@ -627,7 +695,8 @@ struct xg_overlap {
     int64_t n_cand = 0, n_surv = 0, nnz = 0;
     cudaStream_t s = nullptr;
     // device buffers
-    DevBuf tperm, tbox, tpoly, tnv, pairs, surv, area, pos_cnt, row_cnt, ctr;
+    DevBuf tperm, tbox, tpoly, tnv, pairs, surv, prov_col, cnt, prov_ptr, scan_tmp, ctr;
+    size_t scan_tmp_bytes = 0;
     int64_t h_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool stats_valid = false;
     // phase timing: ev[i] is recorded when phase i starts, the last one at the end
@@ -664,8 +733,10 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
     XG_CUDA(cudaMemsetAsync(job->ctr.p, 0, sizeof(unsigned long long) * CTR_N, s));
     XG_CUDA(job->pairs.alloc(sizeof(int2) * (size_t)cap, s));
     XG_CUDA(job->surv.alloc(sizeof(int2) * (size_t)cap, s));
-    XG_CUDA(job->area.alloc(sizeof(double) * (size_t)cap, s));
-    XG_CUDA(cudaMemsetAsync(job->pos_cnt.p, 0, sizeof(int32_t) * (size_t)(n_t + 1), s));
+    XG_CUDA(job->prov_col.alloc(sizeof(int32_t) * (size_t)cap, s));
+    // cnt = [cand_cnt | fill_cnt | row_cnt], (n_t + 1) int32 each
+    XG_CUDA(cudaMemsetAsync(job->cnt.p, 0, sizeof(int32_t) * 2 * (size_t)(n_t + 1), s));
+    int32_t *cand_cnt = job->cnt.as<int32_t>(), *fill_cnt = cand_cnt + (n_t + 1), *row_cnt = fill_cnt + (n_t + 1);
 
     TraverseParams P;
     P.boxes[0] = source->leaf_box; P.count[0] = source->n_face;
@@ -674,8 +745,14 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
     const unsigned tiles = (unsigned)div_up(n_t, 32);
     XG_CUDA(job->mark());  // XG_PHASE_TRAVERSE
     k_traverse<<<(unsigned)div_up(tiles, TRAV_WARPS), TRAV_WARPS * 32, 0, s>>>(
-        P, job->tbox.as<Box>(), n_t, job->pairs.as<int2>(), cap, job->ctr.as<unsigned long long>());
+        P, job->tbox.as<Box>(), n_t, job->pairs.as<int2>(), cap, cand_cnt, job->ctr.as<unsigned long long>());
     XG_CHECK_LAUNCH();
+    {
+        // provisional row starts (sorted target order): a row can hold every candidate of its target
+        cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(cand_cnt, CastI64());
+        size_t tb = job->scan_tmp_bytes;
+        XG_CUDA(cub::DeviceScan::ExclusiveSum(job->scan_tmp.p, tb, it, job->prov_ptr.as<int64_t>(), n_t + 1, s));
+    }
 
     XG_CUDA(job->mark());  // XG_PHASE_SAT
     ClipArgs A;
@@ -683,7 +760,10 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
     A.tpoly = job->tpoly.as<double>(); A.tnv = job->tnv.as<uint8_t>(); A.kt = k_t;
     A.spoly = source->poly; A.snv = source->nvert; A.ks = ks;
     A.surv = job->surv.as<int2>(); A.ctr = job->ctr.as<unsigned long long>();
-    A.area = job->area.as<double>(); A.pos_cnt = job->pos_cnt.as<int32_t>();
+    A.fill_cnt = fill_cnt;
+    A.prov_ptr = job->prov_ptr.as<int64_t>();
+    A.prov_col = job->prov_col.as<int32_t>();
+    A.prov_val = job->pairs.as<double>();  // the candidate arena is dead once k_sat has run (same 8 B per entry)
     if (!job->ev[job->n_ev]) XG_CUDA(cudaEventCreate(&job->ev[job->n_ev]));
     A.between = job->ev[job->n_ev++];  // XG_PHASE_CLIP starts between the two kernels
     int rc;
@@ -702,16 +782,13 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
     if (rc) return rc;
 
     XG_CUDA(job->mark());  // XG_PHASE_ROWPTR
-    k_counts_to_rows<<<(unsigned)div_up(n_t, 256), 256, 0, s>>>(job->pos_cnt.as<int32_t>(), job->tperm.as<int32_t>(),
-                                                               job->t_begin, n_t, job->row_cnt.as<int32_t>());
+    k_counts_to_rows<<<(unsigned)div_up(n_t, 256), 256, 0, s>>>(fill_cnt, job->tperm.as<int32_t>(), job->t_begin,
+                                                               n_t, row_cnt);
     XG_CHECK_LAUNCH();
     {
-        cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(job->row_cnt.as<int32_t>(), CastI64());
-        size_t tb = 0;
-        XG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, d_indptr, n_t + 1, s));
-        DevBuf tmp;
-        XG_CUDA(tmp.alloc(tb, s));
-        XG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, d_indptr, n_t + 1, s));
+        cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(row_cnt, CastI64());
+        size_t tb = job->scan_tmp_bytes;
+        XG_CUDA(cub::DeviceScan::ExclusiveSum(job->scan_tmp.p, tb, it, d_indptr, n_t + 1, s));
     }
     int64_t nnz = 0;
     unsigned long long hc[CTR_N];
@@ -769,8 +846,14 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
         OV_CUDA(job->tbox.alloc(sizeof(Box) * (size_t)n_t, s));
         OV_CUDA(job->tpoly.alloc(sizeof(double) * 2 * (size_t)k_t * (size_t)n_t, s));
         OV_CUDA(job->tnv.alloc((size_t)n_t, s));
-        OV_CUDA(job->row_cnt.alloc(sizeof(int32_t) * (size_t)(n_t + 1), s));
-        OV_CUDA(job->pos_cnt.alloc(sizeof(int32_t) * (size_t)(n_t + 1), s));
+        OV_CUDA(job->cnt.alloc(sizeof(int32_t) * 3 * (size_t)(n_t + 1), s));
+        OV_CUDA(job->prov_ptr.alloc(sizeof(int64_t) * (size_t)(n_t + 1), s));
+        {
+            cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(job->cnt.as<int32_t>(), CastI64());
+            OV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, job->scan_tmp_bytes, it, job->prov_ptr.as<int64_t>(),
+                                                  n_t + 1, s));
+            OV_CUDA(job->scan_tmp.alloc(job->scan_tmp_bytes, s));
+        }
         PackedMesh pm;
         pm.perm = job->tperm.as<int32_t>(); pm.box = job->tbox.as<Box>();
         pm.poly = job->tpoly.as<double>(); pm.nvert = job->tnv.as<uint8_t>();
@@ -806,18 +889,20 @@ extern "C" int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32
     if (job->nnz > 0) {
         if (!d_indices || !d_area || !d_indptr) { set_error("xg_overlap_finish: NULL output"); delete job; return XG_ERR_INVALID; }
         const xg_index *src = job->src;
-        k_scatter<<<NUM_SMS * 8, 256, 0, s>>>(
-            job->surv.as<int2>(), job->area.as<double>(), (unsigned long long)job->n_surv,
-            job->tperm.as<int32_t>(), job->t_begin, src->perm, (const double2 *)src->poly, src->nvert,
-            src->k, relative, d_indptr, job->pos_cnt.as<int32_t>(), d_indices, d_area);
+        RowMove R;
+        int32_t *cand_cnt = job->cnt.as<int32_t>();
+        R.prov_ptr = job->prov_ptr.as<int64_t>(); R.fill_cnt = cand_cnt + (job->n_t + 1);
+        R.prov_col = job->prov_col.as<int32_t>(); R.prov_val = job->pairs.as<double>();
+        R.tperm = job->tperm.as<int32_t>(); R.t_begin = job->t_begin;
+        R.sperm = src->perm; R.spoly = (const double2 *)src->poly; R.snv = src->nvert; R.ks = src->k;
+        R.relative = relative; R.indptr = d_indptr; R.indices = d_indices; R.data = d_area;
         // rows longer than SORT_SHORT are queued in the (now dead) target box buffer
         unsigned long long *n_long = job->ctr.as<unsigned long long>() + CTR_LONG;
         int32_t *long_rows = job->tbox.as<int32_t>();
-        k_sort_rows<<<(unsigned)div_up(job->n_t, 256), 256, 0, s>>>(d_indptr, job->n_t, d_indices, d_area,
-                                                                   long_rows, n_long);
-        k_sort_long_rows<<<NUM_SMS * 4, 128, 0, s>>>(d_indptr, long_rows, n_long, d_indices, d_area);
+        k_move_rows<<<(unsigned)div_up(job->n_t, 256), 256, 0, s>>>(R, job->n_t, long_rows, n_long);
+        k_move_long_rows<<<NUM_SMS * 4, 128, 0, s>>>(R, long_rows, n_long);
         cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) rc = cuda_fail(e, "k_scatter/k_sort_rows", __FILE__, __LINE__);
+        if (e != cudaSuccess) rc = cuda_fail(e, "k_move_rows", __FILE__, __LINE__);
     }
     // buffers are released stream-ordered on the stream that produced them
     if (s != job->s) cudaStreamSynchronize(s);
