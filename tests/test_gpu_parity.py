@@ -374,6 +374,7 @@ def test_overlap_dense_sources_rerun_path(xb):
     txy, tf = synthetic.jittered_lattice(20, 20, 22, "mixed", bounds=(0.03, 0.97, 0.03, 0.97))
     g, tree = gpu_triplets(xb, sxy, sf, txy, tf)
     assert tree.last_stats.candidates > 16 * len(tf)
+    assert tree.last_stats.walks == 2
     assert_same_triplets(g, oracle_triplets(sxy, sf, txy, tf))
     indptr, indices, _ = (t.cpu().numpy() for t in tree.intersect_faces_csr(txy, tf))
     assert np.diff(indptr).max() > 8
@@ -393,6 +394,17 @@ def test_overlap_long_rows_are_sorted(xb, n_coarse, min_row):
     assert np.diff(indptr).max() >= min_row
     rows = np.repeat(np.arange(len(tf)), np.diff(indptr))
     assert np.array_equal(np.lexsort((indices, rows)), np.arange(len(indices)))
+
+
+def test_overlap_fine_source_arena_sized_by_sampling(xb):
+    """a source much finer than the targets: the candidate density is sampled first, so
+    one walk is enough (without it the default arena overflows and the walk runs twice)"""
+    sxy, sf = synthetic.jittered_lattice(420, 420, 51, "tri")
+    txy, tf = synthetic.jittered_lattice(95, 95, 52, "tri", bounds=(0.02, 0.98, 0.02, 0.98))
+    g, tree = gpu_triplets(xb, sxy, sf, txy, tf)
+    assert tree.last_stats.candidates > 16 * len(tf)
+    assert tree.last_stats.walks == 1
+    assert_same_triplets(g, oracle_triplets(sxy, sf, txy, tf))
 
 
 def test_clipped_index_equals_full_index_on_a_target_range(xb):

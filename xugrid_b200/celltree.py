@@ -79,6 +79,7 @@ class OverlapStats(NamedTuple):
     clip_pairs: int
     nnz: int
     candidates: int
+    walks: int = 1  # full walks of the index (2 = the pair arena was too small the first time)
 
 
 class CellTree2d:
@@ -159,7 +160,7 @@ class CellTree2d:
             )
             st = (ctypes.c_int64 * 8)()
             _native.check(L.xg_overlap_stats(job, st))
-            self.last_stats = OverlapStats(*[int(st[i]) for i in range(6)])
+            self.last_stats = OverlapStats(*[int(st[i]) for i in range(7)])
             ms = (ctypes.c_double * 8)()
             _native.check(L.xg_overlap_timings(job, ms))
             self.last_phase_ms = dict(zip(PHASES, [float(ms[i]) for i in range(len(PHASES))]))

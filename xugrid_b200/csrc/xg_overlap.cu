@@ -48,7 +48,7 @@ constexpr int TRAV_QCAP = TRAV_QFLUSH + 32 * TRAV_U;  // pair queue entries per 
 constexpr int PAIRS_PER_TARGET_GUESS = 16;
 
 // device counters of one job
-enum { CTR_VISITS = 0, CTR_TESTS = 1, CTR_PAIRS = 2, CTR_SURV = 3, CTR_LONG = 6, CTR_N = 8 };
+enum { CTR_VISITS = 0, CTR_TESTS = 1, CTR_PAIRS = 2, CTR_SURV = 3, CTR_HUGE = 5, CTR_LONG = 6, CTR_N = 8 };
 
 struct TraverseParams {
     const Box *boxes[MAX_LEVELS + 1];  // [0] = leaves, [d] = node level d-1
@@ -87,7 +87,7 @@ __device__ __forceinline__ void schedule_fence() { asm volatile("" ::: "memory")
 
 // pairs[i] = {sorted target position, sorted source position}
 __global__ void __launch_bounds__(TRAV_WARPS * 32)
-k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t,
+k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t, int tile_stride,
            int2 *__restrict__ pairs, unsigned long long cap, int32_t *__restrict__ cand_cnt,
            unsigned long long *__restrict__ ctr) {
     __shared__ Box s_node[TRAV_WARPS][32];
@@ -95,7 +95,8 @@ k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t,
     __shared__ int2 s_q[TRAV_WARPS][TRAV_QCAP];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int64_t tile = blockIdx.x * (int64_t)TRAV_WARPS + w;
+    // tile_stride > 1: density sampling pass (every tile_stride-th tile, cap == 0: count only)
+    const int64_t tile = (blockIdx.x * (int64_t)TRAV_WARPS + w) * tile_stride;
     const int64_t t = tile * 32 + lane;
     if (tile * 32 >= n_t) return;
     const bool valid = t < n_t;
@@ -186,7 +187,7 @@ k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t,
         __syncwarp();
     }
     if (qn > 0) flush();
-    if (valid) cand_cnt[t] = my_cand;
+    if (valid && cand_cnt) cand_cnt[t] = my_cand;
     if (lane == 0) {
         atomicAdd(ctr + CTR_VISITS, (unsigned long long)visits);
         atomicAdd(ctr + CTR_TESTS, (unsigned long long)tests * 32ull);
@@ -250,8 +251,11 @@ k_sat(const int2 *__restrict__ pairs, unsigned long long cap, const double2 *__r
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     double2 *stg = s_buf + tid;
-    unsigned long long n_pairs = ctr[CTR_PAIRS];
-    if (n_pairs > cap) n_pairs = cap;  // overflowed walk: the job is re-run anyway
+    const unsigned long long n_pairs = ctr[CTR_PAIRS];
+    // overflowed walk: the arena holds only part of the candidates while the provisional
+    // rows were sized for all of them -- nothing downstream may run; the job is re-run
+    // with the exact capacity the walk counted
+    if (n_pairs > cap) return;
     const unsigned long long stride = (unsigned long long)gridDim.x * BT;
 
     auto stage = [&](const int2 r) {
@@ -587,7 +591,8 @@ k_move_rows(const RowMove R, int64_t n_t, int32_t *__restrict__ long_rows,
 // row are distinct, so the rank of a key is its final position)
 __global__ void __launch_bounds__(128)
 k_move_long_rows(const RowMove R, const int32_t *__restrict__ long_rows,
-                 const unsigned long long *__restrict__ n_long) {
+                 const unsigned long long *__restrict__ n_long, int32_t *__restrict__ huge_rows,
+                 unsigned long long *__restrict__ n_huge) {
     __shared__ int32_t s_key[4][SORT_LONG_CAP];
     __shared__ double s_val[4][SORT_LONG_CAP];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -613,29 +618,53 @@ k_move_long_rows(const RowMove R, const int32_t *__restrict__ long_rows,
                 R.data[dst + rank] = s_val[w][i];
             }
             __syncwarp();
-        } else {
-            // beyond any mesh pair seen in practice: copy, then in-place insertion sort by one lane
-            for (int64_t i = lane; i < n; i += 32) {
-                const int32_t s = R.prov_col[src + i];
-                R.indices[dst + i] = R.sperm[s];
-                R.data[dst + i] = entry_value(R, s, R.prov_val[src + i]);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                for (int64_t i = 1; i < n; ++i) {
-                    const int32_t key = R.indices[dst + i];
-                    const double val = R.data[dst + i];
-                    int64_t j = i - 1;
-                    while (j >= 0 && R.indices[dst + j] > key) {
-                        R.indices[dst + j + 1] = R.indices[dst + j];
-                        R.data[dst + j + 1] = R.data[dst + j];
-                        --j;
+        } else if (lane == 0) {
+            // e.g. a sliver on the hull of a Delaunay target that covers thousands of
+            // source faces: a whole block sorts it (k_move_huge_rows)
+            huge_rows[atomicAdd(n_huge, 1ull)] = (int32_t)t;
+        }
+    }
+}
+
+// one block per queued row of more than SORT_LONG_CAP entries: copy to the caller's row,
+// then a bitonic sort in place (global memory, L1/L2 resident).  The network is the
+// variant whose merges all run ascending (first step of a merge compares i with its
+// mirror in the block), so the virtual +inf padding up to the next power of two never
+// moves and needs no storage.
+__global__ void __launch_bounds__(1024)
+k_move_huge_rows(const RowMove R, const int32_t *__restrict__ huge_rows,
+                 const unsigned long long *__restrict__ n_huge) {
+    const unsigned long long total = *n_huge;
+    for (unsigned long long q = blockIdx.x; q < total; q += gridDim.x) {
+        const int64_t t = huge_rows[q];
+        const int64_t n = R.fill_cnt[t];
+        const int64_t src = R.prov_ptr[t];
+        int32_t *key = R.indices + R.indptr[R.tperm[t] - R.t_begin];
+        double *val = R.data + R.indptr[R.tperm[t] - R.t_begin];
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const int32_t s = R.prov_col[src + i];
+            key[i] = R.sperm[s];
+            val[i] = entry_value(R, s, R.prov_val[src + i]);
+        }
+        __syncthreads();
+        int64_t P = 1;
+        while (P < n) P <<= 1;
+        for (int64_t k = 2; k <= P; k <<= 1) {
+            for (int64_t j = k >> 1; j > 0; j >>= 1) {
+                const bool flip = (j == (k >> 1));
+                for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+                    const int64_t p = flip ? (i ^ (k - 1)) : (i ^ j);
+                    if (p > i && p < n) {
+                        const int32_t ki = key[i], kp = key[p];
+                        if (ki > kp) {
+                            const double vi = val[i], vp = val[p];
+                            key[i] = kp; key[p] = ki;
+                            val[i] = vp; val[p] = vi;
+                        }
                     }
-                    R.indices[dst + j + 1] = key;
-                    R.data[dst + j + 1] = val;
                 }
+                __syncthreads();
             }
-            __syncwarp();
         }
     }
 }
@@ -720,6 +749,34 @@ struct xg_overlap {
     }
 };
 
+static TraverseParams traverse_params(const xg_index *source) {
+    TraverseParams P;
+    P.boxes[0] = source->leaf_box; P.count[0] = source->n_face;
+    for (int l = 0; l < source->n_levels; ++l) { P.boxes[l + 1] = source->level_box[l]; P.count[l + 1] = source->level_n[l]; }
+    P.top = source->n_levels + 1;
+    return P;
+}
+
+// Candidate density of a job whose source mesh is much finer than its targets: walk
+// every SAMPLE_STRIDE-th tile without storing anything and scale the count, so that
+// the pair arena is sized right the first time (otherwise the full walk runs twice).
+constexpr int SAMPLE_STRIDE = 64;
+static int estimate_candidates(xg_overlap *job, unsigned long long *estimate) {
+    cudaStream_t s = job->s;
+    const int64_t tiles = div_up(job->n_t, 32);
+    const int64_t sampled = div_up(tiles, SAMPLE_STRIDE);
+    XG_CUDA(cudaMemsetAsync(job->ctr.p, 0, sizeof(unsigned long long) * CTR_N, s));
+    k_traverse<<<(unsigned)div_up(sampled, TRAV_WARPS), TRAV_WARPS * 32, 0, s>>>(
+        traverse_params(job->src), job->tbox.as<Box>(), job->n_t, SAMPLE_STRIDE, nullptr, 0ull, nullptr,
+        job->ctr.as<unsigned long long>());
+    XG_CHECK_LAUNCH();
+    unsigned long long h = 0;
+    XG_CUDA(cudaMemcpyAsync(&h, job->ctr.as<unsigned long long>() + CTR_PAIRS, sizeof(h), cudaMemcpyDeviceToHost, s));
+    XG_CUDA(cudaStreamSynchronize(s));
+    *estimate = (unsigned long long)((double)h * (double)tiles / (double)sampled * 1.25) + 65536ull;
+    return XG_OK;
+}
+
 // one attempt with a pair arena of `cap` entries; *needed receives the number of
 // candidate pairs the walk found (> cap means: run again with that capacity)
 static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_indptr,
@@ -738,14 +795,11 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
     XG_CUDA(cudaMemsetAsync(job->cnt.p, 0, sizeof(int32_t) * 2 * (size_t)(n_t + 1), s));
     int32_t *cand_cnt = job->cnt.as<int32_t>(), *fill_cnt = cand_cnt + (n_t + 1), *row_cnt = fill_cnt + (n_t + 1);
 
-    TraverseParams P;
-    P.boxes[0] = source->leaf_box; P.count[0] = source->n_face;
-    for (int l = 0; l < source->n_levels; ++l) { P.boxes[l + 1] = source->level_box[l]; P.count[l + 1] = source->level_n[l]; }
-    P.top = source->n_levels + 1;
+    const TraverseParams P = traverse_params(source);
     const unsigned tiles = (unsigned)div_up(n_t, 32);
     XG_CUDA(job->mark());  // XG_PHASE_TRAVERSE
     k_traverse<<<(unsigned)div_up(tiles, TRAV_WARPS), TRAV_WARPS * 32, 0, s>>>(
-        P, job->tbox.as<Box>(), n_t, job->pairs.as<int2>(), cap, cand_cnt, job->ctr.as<unsigned long long>());
+        P, job->tbox.as<Box>(), n_t, 1, job->pairs.as<int2>(), cap, cand_cnt, job->ctr.as<unsigned long long>());
     XG_CHECK_LAUNCH();
     {
         // provisional row starts (sorted target order): a row can hold every candidate of its target
@@ -862,13 +916,21 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
 
         unsigned long long cap = (unsigned long long)n_t * PAIRS_PER_TARGET_GUESS;
         if (cap < 65536) cap = 65536;
+        if (source->n_face > 2 * n_t && n_t >= 32 * SAMPLE_STRIDE * 8) {
+            unsigned long long est = 0;
+            rc = estimate_candidates(job, &est);
+            if (rc) goto fail;
+            if (est > cap) cap = est;
+        }
         unsigned long long needed = 0;
         rc = overlap_attempt(job, cap, d_indptr, &needed);
         if (rc) goto fail;
+        job->h_stats[6] = 1;  // walks over all tiles
         if (needed > cap) {
             // denser than guessed: the first walk counted exactly what is needed
             rc = overlap_attempt(job, needed, d_indptr, &needed);
             if (rc) goto fail;
+            job->h_stats[6] = 2;
         }
         job->stats_valid = true;
         *h_nnz = job->nnz;
@@ -900,7 +962,10 @@ extern "C" int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32
         unsigned long long *n_long = job->ctr.as<unsigned long long>() + CTR_LONG;
         int32_t *long_rows = job->tbox.as<int32_t>();
         k_move_rows<<<(unsigned)div_up(job->n_t, 256), 256, 0, s>>>(R, job->n_t, long_rows, n_long);
-        k_move_long_rows<<<NUM_SMS * 4, 128, 0, s>>>(R, long_rows, n_long);
+        unsigned long long *n_huge = job->ctr.as<unsigned long long>() + CTR_HUGE;
+        int32_t *huge_rows = long_rows + job->n_t;  // second n_t ints of the same 32 * n_t byte buffer
+        k_move_long_rows<<<NUM_SMS * 4, 128, 0, s>>>(R, long_rows, n_long, huge_rows, n_huge);
+        k_move_huge_rows<<<NUM_SMS, 1024, 0, s>>>(R, huge_rows, n_huge);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = cuda_fail(e, "k_move_rows", __FILE__, __LINE__);
     }
