@@ -293,11 +293,12 @@ def run_ours(args) -> int:
         #  k_traverse        one 1 KB node (32 boxes x 32 B) per node visit, one 32 B box per target,
         #                    8 B per candidate pair written
         #  k_sat             per candidate: pair ids (8 B) + both polygons (k*16 B each); 8 B per survivor written
-        #  k_clip_survivors  per survivor: pair ids (8 B) + both polygons, one area (8 B), one row counter (4 B)
+        #  k_clip_survivors  per survivor: pair ids (8 B) + both polygons + provisional row start (8 B),
+        #                    one slot counter (4 B), one provisional entry written (4 + 8 B)
         kern = {
             "k_traverse": (stats.node_visits * 1024 + rows * 32 + stats.candidates * 8, phases.get("traverse")),
             "k_sat<3,3>": (stats.candidates * (8 + 16 * k_t + 16 * k_s) + stats.clip_pairs * 8, phases.get("sat")),
-            "k_clip_survivors<3,3>": (stats.clip_pairs * (8 + 16 * k_t + 16 * k_s + 8 + 4), phases.get("clip")),
+            "k_clip_survivors<3,3>": (stats.clip_pairs * (8 + 16 * k_t + 16 * k_s + 8 + 4 + 12), phases.get("clip")),
         }
         kernels = {}
         for name, (nbytes_k, ms_k) in kern.items():
@@ -329,7 +330,7 @@ def run_ours(args) -> int:
                 "workload": workload_name(args.n_side), "n_source_faces": n_s, "n_target_faces": n_t,
                 "nnz": stats.nnz if world == 1 else None, "sharding": f"target rows [{b},{e}) on rank 0 of {world}",
                 "l2": "inputs (2 x 320 MB meshes + 1.5 GB packed records) exceed the 126 MB L2; no explicit flush",
-                "cub_launches_per_step": 14,
+                "cub_launches_per_step": 12,
             },
             "e2e": {"value": n_t / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
