@@ -124,7 +124,8 @@ int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32_t *d_indic
  * stats[0]=targets stats[1]=wide-node visits (V, one coalesced load of <= 32
  * boxes each) stats[2]=leaf bbox tests (C) stats[3]=pairs that passed the
  * separating-axis filter and reached the clipper (C_clip) stats[4]=nnz
- * stats[5]=bbox candidates.  Valid after xg_overlap_begin. */
+ * stats[5]=bbox candidates stats[6]=full walks of the index (2 when the pair
+ * arena had to be re-sized).  Valid after xg_overlap_begin. */
 int xg_overlap_stats(const xg_overlap *job, int64_t stats[8]);
 /* device time of each phase of xg_overlap_begin in milliseconds (CUDA events on
  * the job's stream), indexed by xg_phase.  Valid after xg_overlap_begin. */
