@@ -321,3 +321,31 @@ def test_chunked_target_upload_gives_the_same_weights(xb):
     for a, b in zip(w4, w1):
         assert np.array_equal(a, b)
     assert np.array_equal(out4, r1.regrid(values), equal_nan=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flip_x,flip_y", [(False, False), (True, False), (False, True)])
+def test_raster_target_as_points_equals_promoted_mesh(xb, flip_x, flip_y):
+    """CentroidLocatorRegridder / BarycentricInterpolator onto a raster use only its cell
+    centres, laid out on the device; same points and weights as the quad mesh the
+    reference promotes the raster to (structured.py:489-501)."""
+    from xugrid_b200 import synthetic
+    from xugrid_b200.regridder import _StructuredAdapter
+
+    sxy, sf = synthetic.delaunay(1500, 3)
+    source = xb.Ugrid2d(sxy[:, 0], sxy[:, 1], -1, sf)
+    x = np.linspace(0.05, 0.95, 37)
+    y = np.linspace(0.1, 0.9, 23)
+    x = x[::-1].copy() if flip_x else x
+    y = y[::-1].copy() if flip_y else y
+    raster = xb.StructuredGrid2d(x, y)
+    adapter = _StructuredAdapter(raster)
+    pts = adapter.centroids_device(torch.device("cuda", 0)).cpu().numpy()
+    mesh = raster.to_ugrid2d()
+    assert np.array_equal(pts, mesh.centroids)
+    values = np.random.default_rng(5).random(len(sf))
+    for cls in (xb.CentroidLocatorRegridder, xb.BarycentricInterpolator):
+        a = cls(source, raster).regrid(values)
+        b = cls(source, mesh).regrid(values)
+        assert a.shape == (23, 37)
+        assert np.array_equal(a.ravel(), np.asarray(b).ravel(), equal_nan=True)

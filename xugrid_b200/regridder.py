@@ -147,7 +147,7 @@ class UnstructuredGrid2d:
     def locate_centroids(self, other: "UnstructuredGrid2d", tolerance: Optional[float] = None):
         """unstructured.py:137-144: (source_index, target_index, ones) device tensors."""
         tree = self.ugrid_topology.celltree
-        idx = tree.locate_points_device(other.ugrid_topology.centroids_device, tolerance)
+        idx = tree.locate_points_device(_target_points(other, tree.device), tolerance)
         inside = idx != -1
         source_index = idx[inside]
         target_index = torch.arange(other.size, dtype=torch.int32, device=idx.device)[inside]
@@ -166,7 +166,7 @@ class UnstructuredGrid2d:
 
         grid = self.ugrid_topology
         xy, faces = grid.device_arrays()
-        points = other.ugrid_topology.centroids_device
+        points = _target_points(other, xy.device)
         topo = voronoi.voronoi_topology(faces, xy, grid.centroids_device)
         vor_tree = CellTree2d(topo.vertices, topo.faces, -1, device=xy.device)
         face_index, weights = vor_tree.compute_barycentric_weights_device(points, tolerance)
@@ -219,6 +219,34 @@ class _StructuredAdapter:
             self._promoted = UnstructuredGrid2d(self.grid.to_ugrid2d())
         return self._promoted
 
+    def centroids_device(self, device) -> torch.Tensor:
+        """Centroids of the promoted quad mesh without building it on the host: the
+        node lattice and the connectivity of Ugrid2d.from_structured_bounds
+        (ugrid2d.py:1894-1912,1973-2034) are laid out on the device with a few
+        tensor ops and go through the same centroid kernel as any other mesh, so the
+        points are bit-identical to those of the host-built mesh (a 4096 x 4096
+        raster costs 0.7 s of numpy on the host, a few ms here)."""
+        if self._promoted is not None:
+            return self._promoted.ugrid_topology.centroids_device
+        from .celltree import face_centroid_device
+        from .grid import bounds1d_to_vertices
+
+        g = self.grid
+        x = torch.from_numpy(bounds1d_to_vertices(g.xbounds.directional_bounds)).to(device)
+        y = torch.from_numpy(bounds1d_to_vertices(g.ybounds.directional_bounds)).to(device)
+        nx, ny = x.numel() - 1, y.numel() - 1
+        xy = torch.stack([x.repeat(ny + 1), y.repeat_interleave(nx + 1)], dim=1).contiguous()
+        linear = torch.arange((ny + 1) * (nx + 1), dtype=torch.int32, device=device).reshape(ny + 1, nx + 1)
+        left, right = slice(None, -1), slice(1, None)
+        lower, upper = slice(None, -1), slice(1, None)
+        if float(x[1]) < float(x[0]):
+            left, right = right, left
+        if float(y[1]) < float(y[0]):
+            lower, upper = upper, lower
+        faces = torch.stack([linear[lower, left].reshape(-1), linear[lower, right].reshape(-1),
+                             linear[upper, right].reshape(-1), linear[upper, left].reshape(-1)], dim=1).contiguous()
+        return face_centroid_device(xy, faces)
+
     def to_dataset(self, name: str) -> dict:
         g = self.grid
         return {
@@ -228,6 +256,14 @@ class _StructuredAdapter:
             f"{name}_ybounds": g.ybounds.bounds,
             f"{name}_type": "StructuredGrid2d",
         }
+
+
+def _target_points(target, device) -> torch.Tensor:
+    """(n, 2) device tensor of the target's face centroids (the query points of
+    CentroidLocatorRegridder and BarycentricInterpolator)."""
+    if isinstance(target, _StructuredAdapter):
+        return target.centroids_device(device)
+    return target.ugrid_topology.centroids_device
 
 
 def setup_grid(obj):
@@ -256,6 +292,7 @@ def _grid_from_dataset(ds: dict, prefix: str):
 class BaseRegridder(abc.ABC):
     _METHODS: Tuple[str, ...] = ()
     _TARGET_CHUNKS = 4  # face ranges a large target mesh is uploaded in
+    _TARGET_AS_POINTS = False  # True: the weights need only the target's face centroids
 
     def __init__(self, source, target, tolerance: Optional[float] = None,
                  target_range: Optional[Tuple[int, int]] = None, sharded_upload: bool = False):
@@ -270,6 +307,11 @@ class BaseRegridder(abc.ABC):
         # start both uploads on the copy stream: the index build over the source
         # overlaps with the transfer of the target
         src_grid = self._source.to_unstructured().ugrid_topology
+        if self._TARGET_AS_POINTS and isinstance(self._target, _StructuredAdapter):
+            # only the cell centres of a raster target are needed: no quad mesh, no upload
+            src_grid.prefetch(sharded=sharded_upload)
+            self._compute_weights(self._source, self._target, tolerance)
+            return
         tgt_grid = self._target.to_unstructured().ugrid_topology
         if target_range is None:
             src_grid.prefetch(sharded=sharded_upload)
@@ -426,11 +468,13 @@ class BaseRegridder(abc.ABC):
 class CentroidLocatorRegridder(BaseRegridder):
     """regridder.py:364-426"""
 
+    _TARGET_AS_POINTS = True
+
     def _compute_weights(self, source, target, tolerance=None):
-        src, tgt = source.to_unstructured(), target.to_unstructured()
         if self._target_range is not None:
             raise NotImplementedError("target_range is only supported by the overlap regridders")
-        source_index, target_index, weight_values = src.locate_centroids(tgt, tolerance)
+        # (a raster target is only needed as points: it is not promoted to a quad mesh)
+        source_index, target_index, weight_values = source.to_unstructured().locate_centroids(target, tolerance)
         self._weights = MatrixCOO(weight_values, target_index.contiguous(), source_index.contiguous(),
                                   target.size, source.size, int(weight_values.numel()))
 
@@ -505,6 +549,7 @@ class BarycentricInterpolator(BaseRegridder):
     """
 
     _METHODS = ("mean",)
+    _TARGET_AS_POINTS = True
 
     def __init__(self, source, target, tolerance: Optional[float] = None):
         super().__init__(source, target, tolerance)
@@ -514,8 +559,8 @@ class BarycentricInterpolator(BaseRegridder):
     def _compute_weights(self, source, target, tolerance=None):
         if self._target_range is not None:
             raise NotImplementedError("target_range is only supported by the overlap regridders")
-        src, tgt = source.to_unstructured(), target.to_unstructured()
-        self._weights = src.barycentric(tgt, tolerance)
+        # (a raster target is only needed as points: it is not promoted to a quad mesh)
+        self._weights = source.to_unstructured().barycentric(target, tolerance)
 
     @classmethod
     def from_weights(cls, weights: dict, target):
