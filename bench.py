@@ -184,8 +184,9 @@ def run_ours(args) -> int:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's version banner off stdout (one JSON line)
+        # NCCL prints its version banner (and warnings) on stdout: send them to stderr so that
+        # stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     sxy, sf, txy, tf, values = make_workload(args.n_side)
