@@ -164,6 +164,20 @@ int xg_face_area(const double *d_xy, const void *d_faces, int idx_bytes, int64_t
 int xg_face_centroid(const double *d_xy, const void *d_faces, int idx_bytes, int64_t n_face,
                      int k, double *d_centroid_xy, void *stream);
 
+/* ---- segments against faces ----------------------------------------------
+ * Replaces CellTree2d.intersect_edges as called from
+ * xugrid/regrid/unstructured.py:203-215 (UnstructuredGrid2d.intersection_length,
+ * the weights of NetworkGridder, xugrid/regrid/gridder.py:66-73): every
+ * (segment, face) pair whose Cyrus-Beck clip has positive length.
+ * d_edges is (n_edge, 2, 2) float64.  Up to `cap` results are written, in no
+ * particular order: d_edge_index / d_face_index (caller's ids) and d_xy
+ * (cap, 2, 2) = the clipped segment.  *h_count receives the number of pairs
+ * found (the stream is synchronised); if it exceeds cap, call again with a
+ * larger capacity. */
+int xg_intersect_edges(const xg_index *index, const double *d_edges, int64_t n_edge, int64_t cap,
+                       int32_t *d_edge_index, int32_t *d_face_index, double *d_xy,
+                       int64_t *h_count, void *stream);
+
 /* ---- weight application ---------------------------------------------------
  * Replaces make_regrid(func)._regrid(source, A, size)
  * (xugrid/regrid/regridder.py:34-69):

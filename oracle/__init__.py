@@ -92,6 +92,9 @@ def lib():
             ctypes.c_void_p, _f64p, _i64p, ctypes.c_int64, ctypes.c_int,
         ]
         L.xo_fetch_result.argtypes = [ctypes.c_void_p, _i64p, _i64p, _f64p]
+        L.xo_intersect_edges.restype = ctypes.c_int64
+        L.xo_intersect_edges.argtypes = [ctypes.c_void_p, _f64p, ctypes.c_int64, ctypes.c_int]
+        L.xo_fetch_edges.argtypes = [ctypes.c_void_p, _i64p, _i64p, _f64p]
         L.xo_locate_points.argtypes = [ctypes.c_void_p, _f64p, ctypes.c_int64, ctypes.c_double, _i64p]
         L.xo_locate_point_all.restype = ctypes.c_int
         L.xo_locate_point_all.argtypes = [
@@ -197,6 +200,18 @@ class CellTree2d:
         f = _faces64(faces, fill_value)
         nnz = lib().xo_intersect_faces(self._h, _p_f64(v), v.shape[0], _p_i64(f), f.shape[0], f.shape[1])
         return self._fetch(int(nnz))
+
+    def intersect_edges(self, edge_coords):
+        """numba_celltree.CellTree2d.intersect_edges: (edge index ascending, face index,
+        intersections (n, 2, 2)); call site /root/reference/xugrid/regrid/unstructured.py:203-215"""
+        e = np.ascontiguousarray(np.asarray(edge_coords, dtype=np.float64).reshape(-1, 2, 2))
+        n = int(lib().xo_intersect_edges(self._h, _p_f64(e), e.shape[0], 0))
+        ii = np.empty(n, dtype=np.int64)
+        jj = np.empty(n, dtype=np.int64)
+        xy = np.empty((n, 2, 2), dtype=np.float64)
+        if n:
+            lib().xo_fetch_edges(self._h, _p_i64(ii), _p_i64(jj), _p_f64(xy))
+        return ii, jj, xy
 
     def intersect_faces_bruteforce(self, vertices, faces, fill_value=-1):
         v = _xy(vertices)

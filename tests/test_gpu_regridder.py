@@ -349,3 +349,76 @@ def test_raster_target_as_points_equals_promoted_mesh(xb, flip_x, flip_y):
         b = cls(source, mesh).regrid(values)
         assert a.shape == (23, 37)
         assert np.array_equal(a.ravel(), np.asarray(b).ravel(), equal_nan=True)
+
+
+def _random_network(n_edge, seed, lo=-0.1, hi=1.1):
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(lo, hi, (n_edge, 2))
+    b = a + rng.normal(0.0, 0.08, (n_edge, 2))
+    return np.stack([a, b], axis=1)
+
+
+@pytest.mark.parametrize("mesh", ["delaunay", "mixed", "hexagons"])
+def test_intersect_edges_parity(xb, mesh):
+    """CellTree2d.intersect_edges against the oracle: same (edge, face) pairs, clipped
+    segments bit-identical (same Cyrus-Beck arithmetic, -fmad=false)"""
+    if mesh == "delaunay":
+        xy, f = synthetic.delaunay(3000, 61)
+        edges = _random_network(4000, 62)
+    elif mesh == "mixed":
+        xy, f = synthetic.jittered_lattice(30, 25, 63, "mixed")
+        edges = _random_network(3000, 64)
+    else:
+        xy, f = cases.hexagon_mesh(6, 5, 0)
+        edges = _random_network(1500, 65, -1.0, 9.0)
+    # also: degenerate (zero-length), NaN and far-away segments
+    edges[7] = edges[7][[0, 0]]
+    edges[11, 0, 0] = np.nan
+    edges[13] += 100.0
+    gi, gf, gxy = xb.CellTree2d(xy, f).intersect_edges(edges)
+    oi, of, oxy = oracle.CellTree2d(xy, f).intersect_edges(edges)
+    assert len(gi) > len(edges) // 2
+    assert np.array_equal(gi, oi) and np.array_equal(gf, of)
+    assert np.array_equal(gxy, oxy)
+
+
+def test_intersect_edges_arena_regrows(xb):
+    """long segments crossing many faces: more pairs than the first arena holds"""
+    xy, f = synthetic.jittered_lattice(60, 60, 66, "tri")
+    rng = np.random.default_rng(67)
+    edges = np.stack([rng.uniform(0, 0.1, (300, 2)), rng.uniform(0.9, 1.0, (300, 2))], axis=1)
+    gi, gf, gxy = xb.CellTree2d(xy, f).intersect_edges(edges)
+    oi, of, oxy = oracle.CellTree2d(xy, f).intersect_edges(edges)
+    assert len(gi) > 4 * len(edges) + 1024
+    assert np.array_equal(gi, oi) and np.array_equal(gf, of) and np.array_equal(gxy, oxy)
+
+
+@pytest.mark.parametrize("structured", [False, True])
+def test_network_gridder_reference_known_answers(xb, structured):
+    # /root/reference/tests/test_regrid/test_network_gridder.py:10-140
+    raster = xb.StructuredGrid2d(np.arange(0.5, 4.5, 1.0), np.arange(3.5, -0.5, -1.0))
+    target = raster if structured else raster.to_ugrid2d()
+    node_xy = np.array([[0.0, 0.0], [1.5, 1.5], [2.5, 1.5], [4.0, 0.0], [4.0, 3.0]])
+    edge_nodes = np.array([[0, 1], [1, 2], [2, 3], [2, 4]])
+    network = xb.Ugrid1d(node_xy[:, 0], node_xy[:, 1], -1, edge_nodes)
+    data = np.array([1.0, 2.0, 4.0, -4.0])
+    gridder = xb.NetworkGridder(network, target, method="mean")
+    assert gridder._weights.n == 16 and gridder._weights.m == 4 and gridder._weights.nnz == 8
+    out = np.asarray(gridder.regrid(data))
+    assert out.shape == ((4, 4) if structured else (16,))
+    assert np.count_nonzero(np.isnan(out)) == 11
+    diag = 0.5 * np.sqrt(2)
+    expected = np.array([1.0, (diag * 1 + 0.5 * 2) / (diag + 0.5),
+                         (0.5 * 2 + diag * -4 + diag * 4) / (2 * diag + 0.5), -4.0, 4.0])
+    # rows of the raster run from y = 3.5 down to 0.5
+    cells = [(3, 0), (2, 1), (2, 2), (1, 3), (3, 3)]
+    got = np.array([out.reshape(4, 4)[r, c] for r, c in cells])
+    assert np.allclose(got, expected)
+    # transient data (test_network_gridder.py:97-120) and the weights round trip
+    both = np.asarray(gridder.regrid(np.stack([data, 2.0 * data])))
+    assert np.count_nonzero(np.isnan(both)) == 22
+    assert np.allclose(both.reshape(2, 4, 4)[1][tuple(zip(*cells))], 2.0 * expected)
+    again = xb.NetworkGridder.from_weights(gridder.weights, target, method="mean")
+    assert np.array_equal(np.asarray(again.regrid(data)), out, equal_nan=True)
+    with pytest.raises(TypeError):
+        xb.NetworkGridder(raster.to_ugrid2d(), target)

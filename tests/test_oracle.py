@@ -142,3 +142,44 @@ def test_empty_inputs():
     ti, si, w = tree.intersect_faces(xy + 100.0, faces)
     assert ti.size == 0 and si.size == 0 and w.size == 0
     assert np.array_equal(tree.locate_points(np.array([[50.0, 50.0]])), [-1])
+
+
+def test_intersect_edges_reference_known_answer():
+    """/root/reference/tests/test_regrid/test_network_gridder.py:10-95: a 4x4 raster of unit
+    cells (y descending) and a 4-edge network; nnz == 8 (point contacts do not count) and the
+    length-weighted means the reference expects in five cells."""
+    from xugrid_b200.grid import StructuredGrid2d
+
+    g = StructuredGrid2d(np.arange(0.5, 4.5, 1.0), np.arange(3.5, -0.5, -1.0)).to_ugrid2d()
+    node_xy = np.array([[0.0, 0.0], [1.5, 1.5], [2.5, 1.5], [4.0, 0.0], [4.0, 3.0]])
+    edge_nodes = np.array([[0, 1], [1, 2], [2, 3], [2, 4]])
+    values = np.array([1.0, 2.0, 4.0, -4.0])
+    tree = oracle.CellTree2d(g.node_coordinates, g.face_node_connectivity)
+    ei, fi, xy = tree.intersect_edges(node_xy[edge_nodes])
+    assert len(ei) == 8
+    assert np.array_equal(np.lexsort((fi, ei)), np.arange(8))
+    length = np.linalg.norm(xy[:, 1] - xy[:, 0], axis=1)
+    order = np.lexsort((ei, fi))
+    indptr = oracle.coo_to_csr(fi[order], g.n_face)
+    out = oracle.csr_apply("mean", values[None, :], length[order], ei[order], indptr, g.n_face)[0]
+    assert np.count_nonzero(np.isnan(out)) == 11
+    diag = 0.5 * np.sqrt(2)
+    expected = np.array([1.0, (diag * 1 + 0.5 * 2) / (diag + 0.5),
+                         (0.5 * 2 + diag * -4 + diag * 4) / (2 * diag + 0.5), -4.0, 4.0])
+    cen = oracle.face_centroids(g.node_coordinates, g.face_node_connectivity)
+    x_loc = np.array([0.5, 1.5, 2.5, 3.5, 3.5])
+    y_loc = np.array([0.5, 1.5, 1.5, 2.5, 0.5])
+    cells = [int(np.argmin((cen[:, 0] - x) ** 2 + (cen[:, 1] - y) ** 2)) for x, y in zip(x_loc, y_loc)]
+    assert np.allclose(out[cells], expected)
+
+
+def test_intersect_edges_segment_on_shared_edge_counts_once():
+    """a segment lying on the edge shared by two faces belongs to the face on its left"""
+    xy = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0], [0.0, 1.0], [1.0, 1.0], [2.0, 1.0]])
+    faces = np.array([[0, 1, 4, 3], [1, 2, 5, 4]])
+    tree = oracle.CellTree2d(xy, faces)
+    up = np.array([[[1.0, 0.2], [1.0, 0.8]]])      # direction +y: the left face is face 0
+    ei, fi, seg = tree.intersect_edges(up)
+    assert fi.tolist() == [0] and np.allclose(seg[0], up[0])
+    ei, fi, seg = tree.intersect_edges(up[:, ::-1])  # direction -y: the left face is face 1
+    assert fi.tolist() == [1]

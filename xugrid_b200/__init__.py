@@ -1,15 +1,16 @@
 """
 xugrid_b200 -- B200-native regridding engine behind the xugrid.regrid API
 (OverlapRegridder, RelativeOverlapRegridder, CentroidLocatorRegridder,
-BarycentricInterpolator).  The compute path is hand-written sm_100a CUDA in
+BarycentricInterpolator, NetworkGridder).  The compute path is hand-written sm_100a CUDA in
 libxgregrid.so (C ABI in include/xg_regrid.h); there is no CPU fallback.
 """
 
-from .grid import StructuredGrid2d, Ugrid2d, UgridDataArray  # noqa: F401
+from .grid import StructuredGrid2d, Ugrid1d, Ugrid2d, UgridDataArray  # noqa: F401
 from .celltree import CellTree2d  # noqa: F401
 from .regridder import (  # noqa: F401
     BarycentricInterpolator,
     CentroidLocatorRegridder,
+    NetworkGridder,
     OverlapRegridder,
     RelativeOverlapRegridder,
     create_percentile_method,

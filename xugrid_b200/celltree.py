@@ -184,6 +184,38 @@ class CellTree2d:
         )
         return rows.cpu().numpy(), indices.to(torch.int64).cpu().numpy(), area.cpu().numpy()
 
+    # ------------------------------------------------------------------ segments
+    def intersect_edges_device(self, edge_coords: ArrayLike):
+        """(edge index int32, face index int32, intersections (n, 2, 2) float64) device
+        tensors in ascending (edge, face) order."""
+        L = _native.lib()
+        with torch.cuda.device(self.device):
+            e = to_device(edge_coords, torch.float64, self.device).reshape(-1, 2, 2).contiguous()
+            n_edge = int(e.shape[0])
+            cap = 4 * n_edge + 1024
+            while True:
+                ei = torch.empty(cap, dtype=torch.int32, device=self.device)
+                fi = torch.empty(cap, dtype=torch.int32, device=self.device)
+                xy = torch.empty((cap, 2, 2), dtype=torch.float64, device=self.device)
+                count = ctypes.c_int64()
+                _native.check(
+                    L.xg_intersect_edges(self._h, _native.ptr(e), n_edge, cap, _native.ptr(ei), _native.ptr(fi),
+                                         _native.ptr(xy), ctypes.byref(count), _native.stream_ptr())
+                )
+                if count.value <= cap:
+                    break
+                cap = int(count.value)  # denser than guessed: the first pass counted exactly
+            n = int(count.value)
+            ei, fi, xy = ei[:n], fi[:n], xy[:n]
+            order = torch.argsort(ei.to(torch.int64) * max(self.n_face, 1) + fi.to(torch.int64))
+            return ei[order], fi[order], xy[order]
+
+    def intersect_edges(self, edge_coords: ArrayLike):
+        """numba_celltree-compatible: (edge index ascending, face index, intersections
+        (n, 2, 2)) as numpy int64/int64/float64 (call site: unstructured.py:203-215)."""
+        ei, fi, xy = self.intersect_edges_device(edge_coords)
+        return ei.to(torch.int64).cpu().numpy(), fi.to(torch.int64).cpu().numpy(), xy.cpu().numpy()
+
     # ------------------------------------------------------------------ points
     def locate_points_device(self, points: ArrayLike, tolerance: Optional[float] = None) -> torch.Tensor:
         L = _native.lib()

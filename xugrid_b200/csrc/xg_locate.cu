@@ -166,6 +166,140 @@ k_barycentric(const double2 *__restrict__ pts, int64_t n, const int32_t *__restr
     for (int j = 0; j < len; ++j) wout[flip ? len - 1 - j : j] = w[j];
 }
 
+// ---- intersect_edges: line segments against the faces --------------------------------
+// Replaces CellTree2d.intersect_edges as called from
+// /root/reference/xugrid/regrid/unstructured.py:203-215 (NetworkGridder weights = length
+// of every network edge inside every face).  Same walk as k_locate with lane = segment
+// (Morton order of the midpoints, closed box tests) and Cyrus-Beck parametric clipping
+// against the packed CCW polygon; arithmetic and tie rules as oracle/xg_oracle.c::cyrus_beck.
+__global__ void __launch_bounds__(256)
+k_edge_keys(const double4 *__restrict__ edges, int64_t n, const double *__restrict__ frame,
+            uint32_t *__restrict__ keys, int32_t *__restrict__ ids) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 e = edges[i];
+    const double fx0 = frame[0], fx1 = frame[1], fy0 = frame[2], fy1 = frame[3];
+    const double sx = fx1 > fx0 ? 65536.0 / (fx1 - fx0) : 0.0;
+    const double sy = fy1 > fy0 ? 65536.0 / (fy1 - fy0) : 0.0;
+    double qx = (0.5 * (e.x + e.z) - fx0) * sx, qy = (0.5 * (e.y + e.w) - fy0) * sy;
+    qx = fmin(fmax(qx, 0.0), 65535.0);
+    qy = fmin(fmax(qy, 0.0), 65535.0);
+    keys[i] = spread16p((uint32_t)qx) | (spread16p((uint32_t)qy) << 1);
+    ids[i] = (int32_t)i;
+}
+
+__device__ __forceinline__ bool boxes_touch(const Box &a, const Box &b) {
+    return (a.xmin <= b.xmax) & (b.xmin <= a.xmax) & (a.ymin <= b.ymax) & (b.ymin <= a.ymax);
+}
+
+// segment a + t (b - a), t in [0, 1], clipped by the half planes of a CCW polygon
+__device__ __forceinline__ bool cyrus_beck(double ax, double ay, double bx, double by,
+                                           const double2 *__restrict__ poly, int n, double4 *out) {
+    const double sx = bx - ax, sy = by - ay;
+    double t0 = 0.0, t1 = 1.0;
+    double2 q0 = poly[n - 1];
+    for (int i = 0; i < n; ++i) {
+        const double2 q1 = poly[i];
+        const double ex = q1.x - q0.x, ey = q1.y - q0.y;
+        if (!(ex == 0.0 && ey == 0.0)) {
+            const double nx = -ey, ny = ex;  // inward normal
+            const double num = nx * (ax - q0.x) + ny * (ay - q0.y);
+            const double den = nx * sx + ny * sy;
+            if (den == 0.0) {
+                if (num < 0.0) return false;                                  // parallel, outside
+                if (num == 0.0 && !(ex * sx + ey * sy > 0.0)) return false;  // on the edge, face on the right
+            } else {
+                const double t = -num / den;
+                if (den > 0.0) t0 = t > t0 ? t : t0;  // entering
+                else t1 = t < t1 ? t : t1;            // leaving
+            }
+        }
+        q0 = q1;
+    }
+    if (!(t0 < t1)) return false;
+    *out = make_double4(ax + t0 * sx, ay + t0 * sy, ax + t1 * sx, ay + t1 * sy);
+    return true;
+}
+
+__global__ void __launch_bounds__(LOC_WARPS * 32)
+k_intersect_edges(const LocateParams P, const double4 *__restrict__ edges, const int32_t *__restrict__ order,
+                  int64_t n, const double2 *__restrict__ poly, const uint8_t *__restrict__ nvert, int k,
+                  const int32_t *__restrict__ perm, unsigned long long cap,
+                  unsigned long long *__restrict__ counter, int32_t *__restrict__ edge_out,
+                  int32_t *__restrict__ face_out, double4 *__restrict__ xy_out) {
+    __shared__ Box s_node[LOC_WARPS][32];
+    __shared__ int32_t s_stack[LOC_WARPS][LOC_STACK];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = blockIdx.x * (int64_t)LOC_WARPS + w;
+    const int64_t i = tile * 32 + lane;
+    if (tile * 32 >= n) return;
+    const bool valid = i < n;
+    const int32_t orig = valid ? order[i] : -1;
+    double4 e = make_double4(NAN, NAN, NAN, NAN);
+    if (valid) e = edges[orig];
+    Box qb;  // NaN coordinates give an empty box: never matches
+    qb.xmin = fmin(e.x, e.z); qb.xmax = fmax(e.x, e.z);
+    qb.ymin = fmin(e.y, e.w); qb.ymax = fmax(e.y, e.w);
+    const bool ok = valid && (e.x == e.x) && (e.y == e.y) && (e.z == e.z) && (e.w == e.w);
+    if (!ok) { qb.xmin = INFINITY; qb.xmax = -INFINITY; qb.ymin = INFINITY; qb.ymax = -INFINITY; }
+    Box ub = qb;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ub.xmin = fmin(ub.xmin, __shfl_xor_sync(0xffffffffu, ub.xmin, o));
+        ub.xmax = fmax(ub.xmax, __shfl_xor_sync(0xffffffffu, ub.xmax, o));
+        ub.ymin = fmin(ub.ymin, __shfl_xor_sync(0xffffffffu, ub.ymin, o));
+        ub.ymax = fmax(ub.ymax, __shfl_xor_sync(0xffffffffu, ub.ymax, o));
+    }
+    int sp = 1;
+    if (lane == 0) s_stack[w][0] = P.top << 27;
+    __syncwarp();
+    while (sp > 0) {
+        const int32_t entry = s_stack[w][--sp];
+        const int d = entry >> 27;
+        const int64_t c0 = (int64_t)(entry & 0x7ffffff) * FANOUT;
+        const Box *cb = P.boxes[d - 1];
+        const int64_t nc = P.count[d - 1] - c0;
+        Box mine;
+        if (lane < nc) mine = cb[c0 + lane];
+        else { mine.xmin = INFINITY; mine.xmax = -INFINITY; mine.ymin = INFINITY; mine.ymax = -INFINITY; }
+        unsigned m = __ballot_sync(0xffffffffu, boxes_touch(mine, ub));
+        __syncwarp();
+        if (m == 0) continue;
+        s_node[w][lane] = mine;
+        __syncwarp();
+        if (d > 1) {
+            while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                const Box b = s_node[w][c];
+                if (__any_sync(0xffffffffu, boxes_touch(qb, b))) {
+                    if (lane == 0) s_stack[w][sp] = ((d - 1) << 27) | (int32_t)(c0 + c);
+                    ++sp;
+                }
+            }
+        } else {
+            while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                const Box b = s_node[w][c];
+                if (boxes_touch(qb, b)) {
+                    const int64_t pos = c0 + c;
+                    double4 seg;
+                    if (cyrus_beck(e.x, e.y, e.z, e.w, poly + pos * k, nvert[pos] & 0x7f, &seg)) {
+                        const unsigned long long slot = atomicAdd(counter, 1ull);
+                        if (slot < cap) {
+                            edge_out[slot] = orig;
+                            face_out[slot] = perm[pos];
+                            xy_out[slot] = seg;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 static int locate_impl(const xg_index *ix, const double *d_points, int64_t n, double tol,
                        int32_t *d_face, int32_t *d_pos, cudaStream_t s) {
     if (n == 0) return XG_OK;
@@ -234,5 +368,51 @@ extern "C" int xg_barycentric(const xg_index *index, const double *d_points, int
         (const double2 *)d_points, n_point, pos.as<int32_t>(), (const double2 *)index->poly,
         index->nvert, index->k, tol, d_weights);
     XG_CHECK_LAUNCH();
+    return XG_OK;
+}
+
+extern "C" int xg_intersect_edges(const xg_index *index, const double *d_edges, int64_t n_edge,
+                                  int64_t cap, int32_t *d_edge_index, int32_t *d_face_index,
+                                  double *d_xy, int64_t *h_count, void *stream) {
+    if (!index || !h_count || n_edge < 0 || cap < 0 || (n_edge > 0 && !d_edges) ||
+        (cap > 0 && (!d_edge_index || !d_face_index || !d_xy))) {
+        set_error("xg_intersect_edges: invalid argument");
+        return XG_ERR_INVALID;
+    }
+    if (n_edge >= (int64_t)1 << 31) { set_error("xg_intersect_edges: more than 2^31 edges"); return XG_ERR_UNSUPPORTED; }
+    *h_count = 0;
+    if (n_edge == 0 || index->n_face == 0) return XG_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = n_edge;
+    DevBuf keys_in, keys_out, ids_in, order, tmp, counter;
+    XG_CUDA(keys_in.alloc(sizeof(uint32_t) * (size_t)n, s));
+    XG_CUDA(keys_out.alloc(sizeof(uint32_t) * (size_t)n, s));
+    XG_CUDA(ids_in.alloc(sizeof(int32_t) * (size_t)n, s));
+    XG_CUDA(order.alloc(sizeof(int32_t) * (size_t)n, s));
+    XG_CUDA(counter.alloc(sizeof(unsigned long long), s));
+    XG_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), s));
+    k_edge_keys<<<(unsigned)div_up(n, 256), 256, 0, s>>>((const double4 *)d_edges, n, index->d_frame,
+                                                        keys_in.as<uint32_t>(), ids_in.as<int32_t>());
+    XG_CHECK_LAUNCH();
+    size_t tb = 0;
+    XG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in.as<uint32_t>(), keys_out.as<uint32_t>(),
+                                            ids_in.as<int32_t>(), order.as<int32_t>(), n, 0, 32, s));
+    XG_CUDA(tmp.alloc(tb, s));
+    XG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys_in.as<uint32_t>(), keys_out.as<uint32_t>(),
+                                            ids_in.as<int32_t>(), order.as<int32_t>(), n, 0, 32, s));
+    LocateParams P;
+    P.boxes[0] = index->leaf_box; P.count[0] = index->n_face;
+    for (int l = 0; l < index->n_levels; ++l) { P.boxes[l + 1] = index->level_box[l]; P.count[l + 1] = index->level_n[l]; }
+    P.top = index->n_levels + 1;
+    const unsigned tiles = (unsigned)div_up(n, 32);
+    k_intersect_edges<<<(unsigned)div_up(tiles, LOC_WARPS), LOC_WARPS * 32, 0, s>>>(
+        P, (const double4 *)d_edges, order.as<int32_t>(), n, (const double2 *)index->poly, index->nvert,
+        index->k, index->perm, (unsigned long long)cap, counter.as<unsigned long long>(), d_edge_index,
+        d_face_index, (double4 *)d_xy);
+    XG_CHECK_LAUNCH();
+    unsigned long long h = 0;
+    XG_CUDA(cudaMemcpyAsync(&h, counter.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    XG_CUDA(cudaStreamSynchronize(s));
+    *h_count = (int64_t)h;
     return XG_OK;
 }

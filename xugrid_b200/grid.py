@@ -330,6 +330,54 @@ class Ugrid2d:
         return Ugrid2d._from_intervals_helper(node_x, node_y, nx, ny, name)
 
 
+class Ugrid1d:
+    """The part of xugrid.Ugrid1d the NetworkGridder touches
+    (/root/reference/xugrid/ugrid/ugrid1d.py: node coordinates + edge_node_connectivity,
+    ``edge_node_coordinates``, ``edge_length``, ``edge_dimension``)."""
+
+    def __init__(self, node_x, node_y, fill_value: int, edge_node_connectivity, name: str = "network1d"):
+        self.node_x = np.ascontiguousarray(_host(node_x), dtype=np.float64)
+        self.node_y = np.ascontiguousarray(_host(node_y), dtype=np.float64)
+        if self.node_x.ndim != 1 or self.node_x.shape != self.node_y.shape:
+            raise ValueError("node_x and node_y must be 1D arrays of equal length")
+        conn = np.array(_host(edge_node_connectivity), copy=True)
+        if conn.ndim != 2 or conn.shape[1] != 2:
+            raise ValueError("edge_node_connectivity must be (n_edge, 2)")
+        self.edge_node_connectivity = conn.astype(np.int64)
+        self.fill_value = fill_value
+        self.name = name
+
+    @property
+    def n_node(self) -> int:
+        return self.node_x.size
+
+    @property
+    def n_edge(self) -> int:
+        return self.edge_node_connectivity.shape[0]
+
+    @property
+    def edge_dimension(self) -> str:
+        return f"{self.name}_nEdges"
+
+    @property
+    def core_dimension(self) -> str:
+        return self.edge_dimension
+
+    @property
+    def node_coordinates(self) -> np.ndarray:
+        return np.column_stack([self.node_x, self.node_y])
+
+    @property
+    def edge_node_coordinates(self) -> np.ndarray:
+        """(n_edge, 2, 2): start and end point of every edge"""
+        return self.node_coordinates[self.edge_node_connectivity]
+
+    @property
+    def edge_length(self) -> np.ndarray:
+        xy = self.edge_node_coordinates
+        return np.linalg.norm(xy[:, 1] - xy[:, 0], axis=1)
+
+
 _COPY_STREAMS = {}
 
 
@@ -440,17 +488,19 @@ class StructuredGrid2d:
 
 
 class UgridDataArray:
-    """Face data on a mesh: the small part of xugrid.UgridDataArray the
-    regridders need (values whose LAST axis is the face dimension)."""
+    """Face data on a mesh (or edge data on a Ugrid1d network): the small part of
+    xugrid.UgridDataArray the regridders need (values whose LAST axis is the core
+    dimension of the grid)."""
 
-    def __init__(self, data, grid: Ugrid2d, dims: Optional[Tuple[str, ...]] = None):
+    def __init__(self, data, grid, dims: Optional[Tuple[str, ...]] = None):
         self.data = data
         self.grid = grid
         nd = data.ndim if hasattr(data, "ndim") else np.ndim(data)
-        if data.shape[-1] != grid.n_face:
+        n_core = grid.n_edge if isinstance(grid, Ugrid1d) else grid.n_face
+        if data.shape[-1] != n_core:
             raise ValueError("last axis of data must be the face dimension")
         self.dims = tuple(dims) if dims is not None else tuple(
-            [f"dim_{i}" for i in range(nd - 1)] + [grid.face_dimension]
+            [f"dim_{i}" for i in range(nd - 1)] + [grid.core_dimension]
         )
 
     @property

@@ -28,7 +28,7 @@ import numpy as np
 import torch
 
 from . import sparse
-from .grid import StructuredGrid2d, Ugrid2d, UgridDataArray
+from .grid import StructuredGrid2d, Ugrid1d, Ugrid2d, UgridDataArray
 from .sparse import MatrixCOO, MatrixCSR
 
 
@@ -183,6 +183,17 @@ class UnstructuredGrid2d:
         data = weights[keep]
         return MatrixCSR(data, indices, indptr, other.size, self.size, int(data.numel()))
 
+    def intersection_length(self, other: "Network1d", relative: bool):
+        """unstructured.py:203-215: (target face index, source edge index, length of the
+        edge inside the face) device tensors, ordered by source edge."""
+        edges = torch.from_numpy(other.ugrid_topology.edge_node_coordinates)
+        ei, fi, xy = self.ugrid_topology.celltree.intersect_edges_device(edges)
+        d = xy[:, 1, :] - xy[:, 0, :]
+        length = torch.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
+        if relative:
+            length = length / torch.from_numpy(other.length).to(length.device)[ei.long()]
+        return fi, ei, length
+
     def to_dataset(self, name: str) -> dict:
         g = self.ugrid_topology
         return {
@@ -272,7 +283,7 @@ def setup_grid(obj):
         return UnstructuredGrid2d(obj)
     elif isinstance(obj, StructuredGrid2d):
         return _StructuredAdapter(obj)
-    elif isinstance(obj, (UnstructuredGrid2d, _StructuredAdapter)):
+    elif isinstance(obj, (UnstructuredGrid2d, _StructuredAdapter, Network1d)):
         return obj
     else:
         raise TypeError(
@@ -282,6 +293,9 @@ def setup_grid(obj):
 
 def _grid_from_dataset(ds: dict, prefix: str):
     kind = ds[f"{prefix}_type"]
+    if kind == "Network1d":
+        return Network1d(Ugrid1d(ds[f"{prefix}_node_x"], ds[f"{prefix}_node_y"], -1,
+                                 ds[f"{prefix}_edge_node_connectivity"]))
     if kind == "UnstructuredGrid2d":
         return Ugrid2d(ds[f"{prefix}_node_x"], ds[f"{prefix}_node_y"], -1,
                        ds[f"{prefix}_face_node_connectivity"])
@@ -566,4 +580,84 @@ class BarycentricInterpolator(BaseRegridder):
     def from_weights(cls, weights: dict, target):
         instance = super().from_weights(weights, target)
         instance._setup_regrid("mean")
+        return instance
+
+
+class Network1d:
+    """regrid/network.py:4-38"""
+
+    ndim = 1
+
+    def __init__(self, obj):
+        if isinstance(obj, UgridDataArray) and isinstance(obj.grid, Ugrid1d):
+            self.ugrid_topology = obj.grid
+        elif isinstance(obj, Ugrid1d):
+            self.ugrid_topology = obj
+        else:
+            options = {"Ugrid1d", "UgridDataArray"}
+            raise TypeError(f"Expected one of {options}, received: {type(obj).__name__}")
+
+    @property
+    def dims(self):
+        return (self.ugrid_topology.edge_dimension,)
+
+    @property
+    def shape(self):
+        return (self.ugrid_topology.n_edge,)
+
+    @property
+    def size(self):
+        return self.ugrid_topology.n_edge
+
+    @property
+    def length(self):
+        return self.ugrid_topology.edge_length
+
+    def to_unstructured(self):
+        return self
+
+    def to_dataset(self, name: str) -> dict:
+        g = self.ugrid_topology
+        return {
+            f"{name}_node_x": g.node_x,
+            f"{name}_node_y": g.node_y,
+            f"{name}_edge_node_connectivity": g.edge_node_connectivity,
+            f"{name}_type": "Network1d",
+        }
+
+
+class NetworkGridder(BaseRegridder):
+    """
+    regrid/gridder.py:24-85.  Grids data on the edges of a 1D network onto the faces
+    of a 2D mesh: the weight of (face, edge) is the length of the edge inside the face
+    (``CellTree2d.intersect_edges``, Cyrus-Beck clipping on the GPU), reduced with any
+    of the absolute overlap methods.
+    """
+
+    _METHODS = ABSOLUTE_OVERLAP_METHODS
+
+    def __init__(self, source, target, method: Union[str, Callable] = "mean"):
+        self._source = Network1d(source)
+        self._target = setup_grid(target)
+        self._weights = None
+        self._target_range = None
+        self._compute_weights(self._source, self._target, relative=False)
+        self._setup_regrid(method)
+
+    def _compute_weights(self, source, target, relative: bool = False) -> None:
+        tgt = target.to_unstructured()
+        target_index, source_index, length = tgt.intersection_length(source, relative=relative)
+        # rows = target faces, entries of a row in ascending edge index (sparse.py:119-127)
+        order = torch.argsort(target_index.to(torch.int64) * max(source.size, 1) + source_index.to(torch.int64))
+        self._weights = MatrixCSR.from_triplet(target_index[order], source_index[order], length[order],
+                                               n=target.size, m=source.size)
+
+    @classmethod
+    def _weights_from_dataset(cls, ds: dict):
+        return cls._csr_from_dataset(ds)
+
+    @classmethod
+    def from_weights(cls, weights: dict, target, method: Union[str, Callable] = "mean"):
+        instance = super().from_weights(weights, target)
+        instance._setup_regrid(method)
         return instance
