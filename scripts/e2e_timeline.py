@@ -7,7 +7,10 @@ import xugrid_b200 as xb
 from xugrid_b200 import celltree, synthetic, regridder
 
 n_side = int(sys.argv[1]) if len(sys.argv) > 1 else 2236
-chunks = [int(c) for c in sys.argv[2].split(",")] if len(sys.argv) > 2 else [4]
+# chunk specs separated by ';': an integer (equal chunks) or cumulative fractions "0.125,0.5,1"
+def _spec(t):
+    return int(t) if t.isdigit() else tuple(float(f) for f in t.split(","))
+chunks = [_spec(t) for t in sys.argv[2].split(";")] if len(sys.argv) > 2 else [4]
 sxy, sf = synthetic.jittered_lattice(n_side, n_side, 10, "tri")
 txy, tf = synthetic.jittered_lattice(n_side + 3, n_side - 2, 11, "tri")
 values = torch.from_numpy(np.random.default_rng(12).random((1, sf.shape[0]))).pin_memory()

@@ -153,8 +153,14 @@ class Ugrid2d:
             return
         fb, fe = (0, n) if face_range is None else (max(0, int(face_range[0])), min(n, int(face_range[1])))
         m = max(0, fe - fb)
-        n_chunks = max(1, min(int(n_chunks), m)) if m > 0 else 1
-        bounds = [fb + (m * c) // n_chunks for c in range(n_chunks + 1)]
+        if isinstance(n_chunks, (tuple, list)):
+            # cumulative fractions of the range, e.g. (0.125, 0.5, 1.0): a small first chunk
+            # lets the consumer start early, large later chunks keep its fixed costs low
+            fr = [min(1.0, max(0.0, float(f))) for f in n_chunks]
+            bounds = sorted(set([fb] + [fb + int(round(m * f)) for f in fr] + [fe]))
+        else:
+            n_chunks = max(1, min(int(n_chunks), m)) if m > 0 else 1
+            bounds = [fb + (m * c) // n_chunks for c in range(n_chunks + 1)]
         with torch.cuda.stream(copy_stream):
             if sharded:
                 self._xy_d = sharded_upload(self._xy_pin, dev)
