@@ -178,15 +178,18 @@ def run_ours(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout must carry exactly one JSON line, but native libraries write there too (NCCL
+    # prints its version banner with printf): keep the real stdout aside for the result and
+    # point file descriptor 1 at stderr for everything else
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner (and warnings) on stdout: send them to stderr so that
-        # stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     sxy, sf, txy, tf, values = make_workload(args.n_side)
@@ -354,7 +357,8 @@ def run_ours(args) -> int:
         }
         if world == 1 and not args.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.n_side)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
