@@ -92,3 +92,52 @@ def test_sharded_upload_replicates_a_host_array():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True and q.get(timeout=10) is True
+
+
+def _csr_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from xugrid_b200.distributed import all_gather_csr
+        from xugrid_b200.sparse import MatrixCSR
+
+        sxy, sf = synthetic.delaunay(300, 7)
+        txy, tf = synthetic.jittered_lattice(7, 9, 8, "tri", bounds=(0.1, 0.9, 0.1, 0.9))
+        n_total = len(tf)  # 126 rows over 3 ranks: the last shard is the same size, then try 4 below
+        tree = oracle.CellTree2d(sxy, sf)
+        ok = True
+        for n_rows in (n_total, n_total - 5, 1):
+            b, e = shard_range(n_rows, rank, world)
+            ti, si, w = tree.intersect_faces(txy, tf[b:e]) if e > b else (np.zeros(0, np.int64),) * 2 + (np.zeros(0),)
+            order = np.lexsort((si, ti))
+            ti, si, w = ti[order], si[order], w[order]
+            indptr = oracle.coo_to_csr(ti, e - b)
+            local = MatrixCSR(torch.from_numpy(w), torch.from_numpy(si.astype(np.int32)), torch.from_numpy(indptr),
+                              e - b, len(sf), len(w))
+            full = all_gather_csr(local, n_rows)
+            ti, si, w = tree.intersect_faces(txy, tf[:n_rows])
+            order = np.lexsort((si, ti))
+            ref_ptr = oracle.coo_to_csr(ti[order], n_rows)
+            ok = ok and full.n == n_rows and full.nnz == len(w)
+            ok = ok and np.array_equal(full.indptr.numpy(), ref_ptr)
+            ok = ok and np.array_equal(full.indices.numpy(), si[order])
+            ok = ok and np.array_equal(full.data.numpy(), w[order])
+        q.put(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_all_gather_csr_reassembles_sharded_weights():
+    """three ranks (uneven and empty shards included) gather their CSR rows into the full matrix"""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_csr_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert all(q.get(timeout=10) is True for _ in range(world))

@@ -65,6 +65,53 @@ def all_gather_columns(local: torch.Tensor, n_total: int, group: Optional[dist.P
     return full
 
 
+def all_gather_csr(local, n_total: int, group: Optional[dist.ProcessGroup] = None):
+    """
+    ``local`` is this rank's MatrixCSR over the target rows
+    ``shard_range(n_total, rank, world)``.  Returns the full (n_total rows) MatrixCSR on
+    every rank: the row lengths travel in one all-gather of equally sized slabs, indices
+    and weights in one all-gather each (padded to the largest shard's nnz), and the row
+    pointer is rebuilt by one exclusive scan -- the optional second collective of SURVEY
+    section 8(e), only paid when a caller asks for ``.weights`` of a sharded regridder.
+    """
+    from .sparse import MatrixCSR
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    b, e = shard_range(n_total, rank, world)
+    rows = e - b
+    if local.n != rows:
+        raise ValueError(f"rank {rank} holds {local.n} rows, expected {rows}")
+    dev = local.data.device
+    pad_rows = max_shard(n_total, world)
+    counts = torch.zeros(pad_rows, dtype=torch.int64, device=dev)
+    counts[:rows] = local.indptr[1:] - local.indptr[:-1]
+    all_counts = torch.empty(world * pad_rows, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_counts, counts, group=group)
+    all_counts = all_counts.view(world, pad_rows)
+    nnz_per_rank = all_counts.sum(dim=1)
+    pad_nnz = max(int(nnz_per_rank.max().item()), 1)
+    nnz_local = int(local.data.numel())
+    send_i = torch.zeros(pad_nnz, dtype=local.indices.dtype, device=dev)
+    send_d = torch.zeros(pad_nnz, dtype=local.data.dtype, device=dev)
+    send_i[:nnz_local] = local.indices
+    send_d[:nnz_local] = local.data
+    recv_i = torch.empty(world * pad_nnz, dtype=send_i.dtype, device=dev)
+    recv_d = torch.empty(world * pad_nnz, dtype=send_d.dtype, device=dev)
+    dist.all_gather_into_tensor(recv_i, send_i, group=group)
+    dist.all_gather_into_tensor(recv_d, send_d, group=group)
+    sizes = [int(v) for v in nnz_per_rank.tolist()]
+    indices = torch.cat([recv_i[r * pad_nnz: r * pad_nnz + sizes[r]] for r in range(world)])
+    data = torch.cat([recv_d[r * pad_nnz: r * pad_nnz + sizes[r]] for r in range(world)])
+    row_counts = torch.cat([all_counts[r, : shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0]]
+                            for r in range(world)])
+    indptr = torch.zeros(n_total + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(row_counts, 0, out=indptr[1:])
+    return MatrixCSR(data, indices, indptr, int(n_total), int(local.m), int(data.numel()))
+
+
 def sharded_upload(host: torch.Tensor, device: torch.device,
                    group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
     """

@@ -504,6 +504,17 @@ class CentroidLocatorRegridder(BaseRegridder):
 
 
 class BaseOverlapRegridder(BaseRegridder, abc.ABC):
+    def gather_weights(self, group=None) -> None:
+        """A regridder built with ``target_range`` holds the rows of its own targets only.
+        This collects the rows of all ranks (distributed.all_gather_csr): afterwards
+        ``.weights`` / ``.regrid`` cover the whole target mesh on every rank."""
+        if self._target_range is None:
+            return
+        from .distributed import all_gather_csr
+
+        self._weights = all_gather_csr(self._weights, self._target.size, group)
+        self._target_range = None
+
     def _overlap_weights(self, source, target, relative: bool) -> None:
         # regridder.py:428-436
         src, tgt = source.to_unstructured(), target.to_unstructured()
