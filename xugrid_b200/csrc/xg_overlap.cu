@@ -418,10 +418,10 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
             bool fb = false;
 #ifdef XG_CLIP_DENSE
             ar = clip_area_dense<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT, &fb);
-#elif defined(XG_CLIP_MASKS2)
-            ar = clip_area_masks2<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT, &fb);
-#else
+#elif defined(XG_CLIP_MASKS_BRANCHY)
             ar = clip_area_masks<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT, &fb);
+#else
+            ar = clip_area_masks2<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT, &fb);
 #endif
             if (fb)
                 ar = clip_area_fallback<KT, KS>(tpoly + (int64_t)r_cur.x * kt, na_cur,
