@@ -112,3 +112,34 @@ def test_shard_range_partitions_exactly():
             assert all(a == min(n, r * max_shard(n, world)) for r, (a, _) in enumerate(ranges))
     with pytest.raises(ValueError):
         shard_range(10, 2, 2)
+
+
+def test_recorded_bench_lines_follow_the_contract():
+    """the JSON lines bench.py printed on the B200 (kept under profiles/) carry every key the
+    bench contract names, for our arm and for the reference arm"""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ours = json.load(open(os.path.join(root, "profiles", "r1_bench_n1.json")))
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline",
+                "cpu_baseline", "clocks"):
+        assert key in ours, key
+    assert ours["n_gpus"] == 1 and ours["warmup"] >= 3 and ours["dtype"] == "f64" and ours["vs_baseline"] is None
+    assert "workload" in ours["config"] and "model" not in ours["config"]
+    for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert key in ours["e2e"], key
+    assert ours["e2e"]["h2d_bytes_per_step"] > 0 and ours["e2e"]["value"] < ours["value"]
+    roof = ours["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in roof, key
+    assert roof["bound"] == "hbm" and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
+    for key in ("value", "unit", "cores", "kind", "sample"):
+        assert key in ours["cpu_baseline"], key
+    assert ours["gpu_launches"] > 0
+    assert not set(ours["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    ref = json.load(open(os.path.join(root, "profiles", "r1_bench_reference_arm.json")))
+    assert ref["impl"] == "reference" and ref["metric"] == ours["metric"] and ref["unit"] == ours["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["value"] == ref["value"]
+    assert ref["cpu_baseline"]["kind"] in ("port", "reference")

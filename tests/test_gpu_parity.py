@@ -50,6 +50,9 @@ MESH_PAIRS = {
     "raster_on_raster": lambda: (*synthetic.jittered_lattice(20, 20, 8, "quad", jitter=0.0), *synthetic.jittered_lattice(10, 10, 9, "quad", jitter=0.0)),
     "hexagons_k6": lambda: (*cases.hexagon_mesh(6, 5, 0), *synthetic.jittered_lattice(15, 14, 10, "tri", bounds=(-1.0, 9.0, -1.0, 9.0))),
     "tri_onto_hexagons": lambda: (*synthetic.jittered_lattice(15, 14, 10, "tri", bounds=(-1.0, 9.0, -1.0, 9.0)), *cases.hexagon_mesh(6, 5, 0)),
+    # 61k -> 61k faces: enough pairs that every thread of the persistent SAT / clip grids takes
+    # several grid-stride trips (the software-pipelined loop bodies; smaller cases leave after one)
+    "tri_tri_multi_trip": lambda: (*synthetic.jittered_lattice(175, 175, 12, "tri"), *synthetic.jittered_lattice(173, 178, 13, "tri")),
     "disk_to_coarse": lambda: (*synthetic.disk(), *synthetic.jittered_lattice(10, 10, 11, "quad", jitter=0.0, bounds=(-10.0, 10.0, -10.0, 10.0))),
 }
 
