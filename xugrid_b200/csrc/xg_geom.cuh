@@ -209,128 +209,9 @@ __device__ __forceinline__ bool polygons_intersect_uniform(const double2 (&a)[KA
     return !separated;
 }
 
-// Each clip stage runs as
-//   pass 1  walk the subject once: drop repeated vertices, evaluate `inside`
-//           for every kept vertex, remember where the in/out state flips
-//           (a convex subject flips 0 or 2 times)
-//   pass 2  compute the (at most two) intersection points -- the only
-//           divisions -- for all lanes together
-//   pass 3  emit [intersection, vertex-if-inside] in subject order
-// instead of interleaving an inside test with a rare, division-heavy
-// intersection per vertex.  Configurations the fast path does not cover (more
-// than two flips, or an intersection with a zero denominator, which alters
-// the state the sequential loop carries) set *fallback; the caller re-runs
-// clip_area() for that lane.
-template <int KT, int KS>
-__device__ __forceinline__ double clip_area_dense(const double2 (&poly)[KT], int np,
-                                                  const double2 (&clip)[KS], int nc, double2 *bufA,
-                                                  double2 *bufB, int stride, bool *fallback) {
-    constexpr int M = KT + KS;
-    double2 *out = bufA, *sub = bufB;
-    int n_out = np;
-#pragma unroll
-    for (int i = 0; i < KT; ++i)
-        if (i < np) out[i * stride] = poly[i];
 
-    bool dead = false;  // fewer than 3 vertices left: area 0
-    bool fb = false;
-    double2 r = last_vertex(clip, nc);
-#pragma unroll
-    for (int i = 0; i < KS; ++i) {
-        const double2 s = clip[i];
-        const double Ux = s.x - r.x, Uy = s.y - r.y;
-        const bool run = (i < nc) && !(Ux == 0.0 && Uy == 0.0) && !dead && !fb;
-        if (run) {
-            const double Nx = -Uy, Ny = Ux;
-            double2 *t = sub;
-            sub = out;
-            out = t;
-            const int length = n_out;
-            // ---- pass 1
-            double2 a = sub[(length - 1) * stride];
-            bool a_in = Ux * (a.y - r.y) > Uy * (a.x - r.x);
-            int a_idx = length - 1;
-            unsigned kept = 0u, inm = 0u;
-            int nflip = 0, cj0 = -1, cp0 = 0, cj1 = -1, cp1 = 0;
-#pragma unroll
-            for (int j = 0; j < M; ++j) {
-                if (j < KT + i && j < length) {  // after i clips: at most KT + i vertices
-                    const double2 b = sub[j * stride];
-                    const bool use = !(b.x == a.x && b.y == a.y);
-                    const bool b_in = Ux * (b.y - r.y) > Uy * (b.x - r.x);
-                    const bool flip = use && (b_in != a_in);
-                    const bool first = flip && nflip == 0;
-                    const bool later = flip && nflip != 0;
-                    cj0 = first ? j : cj0;
-                    cp0 = first ? a_idx : cp0;
-                    cj1 = later ? j : cj1;
-                    cp1 = later ? a_idx : cp1;
-                    nflip += flip ? 1 : 0;
-                    kept |= (use ? 1u : 0u) << j;
-                    inm |= ((use && b_in) ? 1u : 0u) << j;
-                    a.x = use ? b.x : a.x;
-                    a.y = use ? b.y : a.y;
-                    a_in = use ? b_in : a_in;
-                    a_idx = use ? j : a_idx;
-                }
-            }
-            fb = fb || nflip > 2;
-            // ---- pass 2
-            double2 X0 = make_double2(0.0, 0.0), X1 = X0;
-            if (nflip > 0) {
-                const double2 pa = sub[cp0 * stride], pb = sub[cj0 * stride];
-                const double Vx = pb.x - pa.x, Vy = pb.y - pa.y;
-                const double Wx = pa.x - r.x, Wy = pa.y - r.y;
-                const double nw = Nx * Wx + Ny * Wy;
-                const double nv = Nx * Vx + Ny * Vy;
-                fb = fb || nv == 0.0;
-                const double tt = -nw / nv;
-                X0 = make_double2(pa.x + tt * Vx, pa.y + tt * Vy);
-            }
-            if (nflip > 1) {
-                const double2 pa = sub[cp1 * stride], pb = sub[cj1 * stride];
-                const double Vx = pb.x - pa.x, Vy = pb.y - pa.y;
-                const double Wx = pa.x - r.x, Wy = pa.y - r.y;
-                const double nw = Nx * Wx + Ny * Wy;
-                const double nv = Nx * Vx + Ny * Vy;
-                fb = fb || nv == 0.0;
-                const double tt = -nw / nv;
-                X1 = make_double2(pa.x + tt * Vx, pa.y + tt * Vy);
-            }
-            // ---- pass 3
-            n_out = 0;
-#pragma unroll
-            for (int j = 0; j < M; ++j) {
-                if (j < KT + i && j < length && ((kept >> j) & 1u)) {
-                    if (j == cj0) { out[n_out * stride] = X0; ++n_out; }
-                    else if (j == cj1) { out[n_out * stride] = X1; ++n_out; }
-                    if ((inm >> j) & 1u) { out[n_out * stride] = sub[j * stride]; ++n_out; }
-                }
-            }
-            dead = n_out < 3;
-            r = s;
-        }
-    }
-    *fallback = fb;
-    if (dead || fb) return 0.0;
-    double area = 0.0;
-    const double2 a0 = out[0];
-    const double2 b0 = out[stride];
-    double Ux = b0.x - a0.x, Uy = b0.y - a0.y;
-#pragma unroll
-    for (int i = 2; i < M; ++i) {
-        if (i < n_out) {
-            const double2 c = out[i * stride];
-            const double Vx = a0.x - c.x, Vy = a0.y - c.y;
-            area += fabs(cross2(Ux, Uy, Vx, Vy));
-            Ux = Vx;
-            Uy = Vy;
-        }
-    }
-    return 0.5 * area;
-}
 
-// Bit-mask formulation of the same clip (the default in k_clip_survivors).
+// Bit-mask formulation of the same clip (what k_clip_survivors runs).
 // For a subject without repeated vertices the sequential Sutherland-Hodgman
 // loop is a pure function of the per-vertex `inside` flags:
 //   * the in/out state flips where inside(j) != inside(j-1) (cyclically);
@@ -340,120 +221,19 @@ __device__ __forceinline__ double clip_area_dense(const double2 (&poly)[KT], int
 // so a stage is: load the subject into registers, one `inside` evaluation per
 // vertex, a handful of integer mask operations, the two intersections (the
 // only divisions, evaluated together), and predicated stores to computed
-// slots -- about half the instructions of clip_area_dense() (measured by
-// smsp__inst_executed, profiles/), with identical floating-point operations.
-// Lanes with a repeated subject vertex, more than two flips or a zero
-// denominator set *fallback and are re-run through clip_area().
+// slots.  The code is straight-line: the two vertex lists have FIXED roles
+// (stage i reads list i & 1 and writes the other one; an unchanged subject is
+// copied through), so no per-lane buffer pointers are swapped, and a stage has
+// no branch on the number of flips: lanes without a crossing run the same
+// instructions with their stores predicated off and a safe denominator.
+// Identical floating-point operations on the lanes that matter, identical
+// results.  Executed instructions per pair (smsp__inst_executed, profiles/):
+// 1 133 for the per-vertex loop this replaced, 880 for a branchy mask version,
+// 750 here.  Lanes with a repeated subject vertex, more than two flips, a zero
+// denominator or a zero-length clip edge set *fallback and are re-run through
+// clip_area().
 template <int KT, int KS>
 __device__ __forceinline__ double clip_area_masks(const double2 (&poly)[KT], int np,
-                                                  const double2 (&clip)[KS], int nc, double2 *bufA,
-                                                  double2 *bufB, int stride, bool *fallback) {
-    constexpr int M = KT + KS;
-    double2 *cur = bufA, *oth = bufB;  // cur holds the subject of the next stage
-    int length = np;
-#pragma unroll
-    for (int i = 0; i < KT; ++i)
-        if (i < np) cur[i * stride] = poly[i];
-
-    bool dead = false, fb = false;
-    double2 r = last_vertex(clip, nc);
-#pragma unroll
-    for (int i = 0; i < KS; ++i) {
-        const double2 s = clip[i];
-        const double Ux = s.x - r.x, Uy = s.y - r.y;
-        const bool run = (i < nc) && !(Ux == 0.0 && Uy == 0.0) && !dead && !fb;
-        if (run) {
-            const double Nx = -Uy, Ny = Ux;
-            // ---- subject into registers (stage 0: it is the caller's polygon)
-            double2 v[M];
-            double2 prev;
-            if (i == 0) {
-#pragma unroll
-                for (int j = 0; j < KT; ++j) v[j] = poly[j];
-                prev = last_vertex(poly, np);
-            } else {
-#pragma unroll
-                for (int j = 0; j < M; ++j)
-                    if (j < KT + i && j < length) v[j] = cur[j * stride];
-                prev = cur[(length - 1) * stride];
-            }
-            unsigned inm = 0u;
-            bool dup = false;
-#pragma unroll
-            for (int j = 0; j < M; ++j)
-                if (j < KT + i && j < length) {
-                    const bool in = Ux * (v[j].y - r.y) > Uy * (v[j].x - r.x);
-                    inm |= (in ? 1u : 0u) << j;
-                    dup = dup || (v[j].x == prev.x && v[j].y == prev.y);
-                    prev = v[j];
-                }
-            const unsigned full = (1u << length) - 1u;
-            const unsigned flipm = (inm ^ ((inm << 1) | (inm >> (length - 1)))) & full;
-            const int nflip = __popc(flipm);
-            fb = dup || nflip > 2;
-            if (nflip == 0) {
-                dead = inm == 0u;  // everything outside; otherwise the subject is unchanged
-            } else if (!fb) {
-                const int cj0 = __ffs(flipm) - 1, cj1 = 31 - __clz(flipm);
-                const int cp0 = cj0 ? cj0 - 1 : length - 1, cp1 = cj1 - 1;
-                const double2 pa0 = cur[cp0 * stride], pb0 = cur[cj0 * stride];
-                const double2 pa1 = cur[cp1 * stride], pb1 = cur[cj1 * stride];
-                const double V0x = pb0.x - pa0.x, V0y = pb0.y - pa0.y;
-                const double V1x = pb1.x - pa1.x, V1y = pb1.y - pa1.y;
-                const double nw0 = Nx * (pa0.x - r.x) + Ny * (pa0.y - r.y);
-                const double nw1 = Nx * (pa1.x - r.x) + Ny * (pa1.y - r.y);
-                const double nv0 = Nx * V0x + Ny * V0y;
-                const double nv1 = Nx * V1x + Ny * V1y;
-                fb = nv0 == 0.0 || nv1 == 0.0;
-                const double t0 = -nw0 / (fb ? 1.0 : nv0);
-                const double t1 = -nw1 / (fb ? 1.0 : nv1);
-                const double2 X0 = make_double2(pa0.x + t0 * V0x, pa0.y + t0 * V0y);
-                const double2 X1 = make_double2(pa1.x + t1 * V1x, pa1.y + t1 * V1y);
-                // ---- emit
-#pragma unroll
-                for (int j = 0; j < M; ++j)
-                    if (j < KT + i && j < length && ((inm >> j) & 1u)) {
-                        const int pos = __popc(inm & ((1u << j) - 1u)) + __popc(flipm & ((2u << j) - 1u));
-                        oth[pos * stride] = v[j];
-                    }
-                oth[__popc(inm & ((1u << cj0) - 1u)) * stride] = X0;
-                oth[(__popc(inm & ((1u << cj1) - 1u)) + 1) * stride] = X1;
-                length = __popc(inm) + 2;
-                double2 *t = cur;
-                cur = oth;
-                oth = t;
-            }
-            r = s;
-        }
-    }
-    *fallback = fb;
-    if (dead || fb) return 0.0;
-    double area = 0.0;
-    const double2 a0 = cur[0];
-    const double2 b0 = cur[stride];
-    double Ux = b0.x - a0.x, Uy = b0.y - a0.y;
-#pragma unroll
-    for (int i = 2; i < M; ++i) {
-        if (i < length) {
-            const double2 c = cur[i * stride];
-            const double Vx = a0.x - c.x, Vy = a0.y - c.y;
-            area += fabs(cross2(Ux, Uy, Vx, Vy));
-            Ux = Vx;
-            Uy = Vy;
-        }
-    }
-    return 0.5 * area;
-}
-
-// Straight-line variant of clip_area_masks(): the two vertex lists have FIXED roles
-// (stage i reads list i & 1 and writes the other one; an unchanged subject is copied
-// through), so no per-lane buffer pointers are swapped, and a stage has no branch on
-// the number of flips: lanes without a crossing run the same instructions with their
-// stores predicated off and a safe denominator.  Same floating-point operations on
-// the lanes that matter, identical results; fewer moves and branch instructions.
-// Stages that the sequential routine would skip (zero-length clip edge) fall back.
-template <int KT, int KS>
-__device__ __forceinline__ double clip_area_masks2(const double2 (&poly)[KT], int np,
                                                    const double2 (&clip)[KS], int nc, double2 *bufA,
                                                    double2 *bufB, int stride, bool *fallback) {
     constexpr int M = KT + KS;

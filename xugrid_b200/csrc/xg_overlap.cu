@@ -214,7 +214,7 @@ __device__ __forceinline__ int load_poly(const double2 *__restrict__ poly, const
 // Both read their element count from device memory and stride over it, so no
 // host round trip separates them from the walk.
 
-// rare slow path of clip_area_dense(), kept out of line so that it does not
+// rare slow path of clip_area_masks(), kept out of line so that it does not
 // cost the main path registers
 template <int KT, int KS>
 __device__ __noinline__ double clip_area_fallback(const double2 *pa, int na, const double2 *pb, int nb,
@@ -416,13 +416,7 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
         double ar;
         if (KT + KS <= 32) {
             bool fb = false;
-#ifdef XG_CLIP_DENSE
-            ar = clip_area_dense<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT, &fb);
-#elif defined(XG_CLIP_MASKS_BRANCHY)
             ar = clip_area_masks<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT, &fb);
-#else
-            ar = clip_area_masks2<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT, &fb);
-#endif
             if (fb)
                 ar = clip_area_fallback<KT, KS>(tpoly + (int64_t)r_cur.x * kt, na_cur,
                                                 spoly + (int64_t)r_cur.y * ks, nb_cur, bufA, bufB, BT);
