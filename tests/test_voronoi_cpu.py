@@ -71,3 +71,18 @@ def test_voronoi_rejects_non_manifold_exterior():
     cent = oracle.face_centroids(xy, faces)
     with pytest.raises(ValueError):
         voronoi.voronoi_topology(torch.from_numpy(faces), torch.from_numpy(xy), torch.from_numpy(cent))
+
+
+def test_single_sort_by_group_then_angle_is_the_exact_lexsort():
+    """the one-pass sort (group id | 32-bit angle) returns the order of the exact two-pass
+    lexsort, also when the quantised angles collide (fallback) and for equal angles (stable)"""
+    rng = np.random.default_rng(0)
+    group = torch.from_numpy(rng.integers(0, 500, 20000))
+    angle = torch.from_numpy(rng.uniform(-np.pi, np.pi, 20000))
+    angle[::97] = angle[1::97][: angle[::97].numel()]          # exact ties
+    assert torch.equal(voronoi._sort_by_group_then_angle(angle, group), voronoi._lexsort(angle, group))
+    close = torch.tensor([0.1, 0.1 + 1e-12, 0.1 - 1e-12, 2.0, -3.0], dtype=torch.float64)
+    g0 = torch.zeros(5, dtype=torch.int64)
+    assert torch.equal(voronoi._sort_by_group_then_angle(close, g0), voronoi._lexsort(close, g0))
+    empty = torch.zeros(0, dtype=torch.float64)
+    assert voronoi._sort_by_group_then_angle(empty, torch.zeros(0, dtype=torch.int64)).numel() == 0

@@ -55,6 +55,23 @@ def _lexsort(minor: torch.Tensor, major: torch.Tensor) -> torch.Tensor:
     return o1[o2]
 
 
+def _sort_by_group_then_angle(angle: torch.Tensor, group: torch.Tensor) -> torch.Tensor:
+    """Order of ``_lexsort(angle, group)`` (group ids >= 0, angles in [-pi, pi]) with ONE
+    sort instead of two: the key is the group id in the high 32 bits and the angle
+    quantised to 32 bits in the low ones.  The result is then checked against the
+    float64 angles (non-decreasing inside every group); a mesh whose angles the
+    quantisation cannot separate falls back to the exact two-pass sort, so the order
+    returned is always the exact one."""
+    if angle.numel() == 0 or int(group.max().item()) >= (1 << 31):
+        return _lexsort(angle, group)
+    q = ((angle + torch.pi) * (4294967295.0 / (2.0 * torch.pi))).clamp_(0.0, 4294967295.0).to(torch.int64)
+    key = (group.to(torch.int64) << 32) | q
+    order = torch.argsort(key, stable=True)
+    a, g = angle[order], group[order]
+    exact = bool(((a[1:] >= a[:-1]) | (g[1:] != g[:-1])).all())
+    return order if exact else _lexsort(angle, group)
+
+
 def _ragged_to_dense(group: torch.Tensor, values: torch.Tensor, n_group: int) -> torch.Tensor:
     """group must be sorted ascending with ids 0..n_group-1; returns (n_group, max_len), -1 fill."""
     counts = torch.bincount(group, minlength=n_group)
@@ -80,8 +97,14 @@ def exterior_edges(faces: torch.Tensor, n_node: int):
     ok = a != b
     a, b, f = a[ok], b[ok], f[ok]
     key = torch.minimum(a, b) * n_node + torch.maximum(a, b)
-    _, inverse, counts = torch.unique(key, return_inverse=True, return_counts=True)
-    ext = counts[inverse] == 1
+    # an edge is exterior when its key occurs once: one sort and a comparison with both
+    # neighbours (torch.unique with inverse and counts sorts too, then makes three more passes)
+    sk, order = torch.sort(key)
+    once = torch.ones_like(sk, dtype=torch.bool)
+    once[1:] &= sk[1:] != sk[:-1]
+    once[:-1] &= sk[:-1] != sk[1:]
+    ext = torch.zeros_like(once)
+    ext[order] = once
     return a[ext], b[ext], f[ext]
 
 
@@ -118,9 +141,9 @@ def voronoi_topology(faces: torch.Tensor, xy: torch.Tensor, centroids: torch.Ten
     interior = ~is_ext[inc_node]
     n_i, f_i = inc_node[interior], inc_face[interior]
     d = centroids[f_i] - xy[n_i]
-    order = _lexsort(torch.atan2(d[:, 1], d[:, 0]), n_i)
+    order = _sort_by_group_then_angle(torch.atan2(d[:, 1], d[:, 0]), n_i)
     n_i, f_i = n_i[order], f_i[order]
-    int_nodes, int_group = torch.unique(n_i, return_inverse=True)
+    int_nodes, int_group = torch.unique_consecutive(n_i, return_inverse=True)  # n_i is sorted
     interior_faces = _ragged_to_dense(int_group, f_i, int_nodes.numel())
 
     # ---- exterior: projections of boundary-face centroids on their exterior edge
