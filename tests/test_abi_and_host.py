@@ -143,3 +143,24 @@ def test_recorded_bench_lines_follow_the_contract():
     assert ref["impl"] == "reference" and ref["metric"] == ours["metric"] and ref["unit"] == ours["unit"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["value"] == ref["value"]
     assert ref["cpu_baseline"]["kind"] in ("port", "reference")
+
+
+def test_ugrid1d_and_network1d_host_logic():
+    # the part of xugrid.Ugrid1d / regrid/network.py:4-38 the NetworkGridder touches
+    from xugrid_b200.regridder import Network1d
+
+    node_xy = np.array([[0.0, 0.0], [3.0, 4.0], [3.0, 0.0]])
+    net = xb.Ugrid1d(node_xy[:, 0], node_xy[:, 1], -1, np.array([[0, 1], [1, 2]]))
+    assert net.n_edge == 2 and net.n_node == 3 and net.edge_dimension == net.core_dimension
+    assert np.array_equal(net.edge_node_coordinates, node_xy[[[0, 1], [1, 2]]])
+    assert np.allclose(net.edge_length, [5.0, 4.0])
+    wrapped = Network1d(net)
+    assert wrapped.size == 2 and wrapped.shape == (2,) and wrapped.ndim == 1
+    data = xb.UgridDataArray(np.array([[1.0, 2.0]]), net)
+    assert Network1d(data).ugrid_topology is net and data.dims[-1] == net.edge_dimension
+    with pytest.raises(TypeError):
+        Network1d(np.zeros(3))
+    with pytest.raises(ValueError):
+        xb.Ugrid1d(node_xy[:, 0], node_xy[:, 1], -1, np.array([[0, 1, 2]]))
+    with pytest.raises(ValueError):
+        xb.UgridDataArray(np.zeros(3), net)

@@ -183,3 +183,50 @@ def test_intersect_edges_segment_on_shared_edge_counts_once():
     assert fi.tolist() == [0] and np.allclose(seg[0], up[0])
     ei, fi, seg = tree.intersect_edges(up[:, ::-1])  # direction -y: the left face is face 1
     assert fi.tolist() == [1]
+
+
+def test_intersect_edges_conserves_length():
+    """segments inside the mesh hull: the clipped pieces of a segment add up to its length"""
+    from xugrid_b200 import synthetic
+
+    xy, f = synthetic.jittered_lattice(20, 17, 71, "mixed")
+    rng = np.random.default_rng(72)
+    a = rng.uniform(0.05, 0.95, (400, 2))
+    b = np.clip(a + rng.normal(0.0, 0.15, (400, 2)), 0.05, 0.95)
+    edges = np.stack([a, b], axis=1)
+    ei, fi, seg = oracle.CellTree2d(xy, f).intersect_edges(edges)
+    piece = np.linalg.norm(seg[:, 1] - seg[:, 0], axis=1)
+    total = np.bincount(ei, weights=piece, minlength=len(edges))
+    assert np.allclose(total, np.linalg.norm(b - a, axis=1), rtol=1e-12, atol=1e-14)
+    # every piece lies on its segment and inside the face's bounding box
+    bb = oracle.build_bboxes(xy, f)[fi]
+    lo = np.minimum(seg[:, 0], seg[:, 1]); hi = np.maximum(seg[:, 0], seg[:, 1])
+    assert (lo[:, 0] >= bb[:, 0] - 1e-12).all() and (hi[:, 0] <= bb[:, 1] + 1e-12).all()
+    assert (lo[:, 1] >= bb[:, 2] - 1e-12).all() and (hi[:, 1] <= bb[:, 3] + 1e-12).all()
+
+
+def test_clip_area_properties():
+    """Sutherland-Hodgman area of random convex polygon pairs: symmetric, bounded by both
+    areas, equal to the polygon's own area when clipped by itself or by a polygon around it"""
+    rng = np.random.default_rng(9)
+
+    def convex(n, cx, cy, r):
+        ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+        return np.column_stack([cx + r * np.cos(ang), cy + r * np.sin(ang)])
+
+    def area(p):
+        x, y = p[:, 0], p[:, 1]
+        return 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+
+    for _ in range(300):
+        a = convex(rng.integers(3, 8), rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(0.3, 1.5))
+        b = convex(rng.integers(3, 8), rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(0.3, 1.5))
+        ab, ba = oracle.clip_area(a, b), oracle.clip_area(b, a)
+        assert abs(ab - ba) <= 1e-12 * max(area(a), area(b))
+        assert ab <= min(area(a), area(b)) * (1 + 1e-12)
+        assert abs(oracle.clip_area(a, a) - area(a)) <= 1e-12 * area(a)
+        t = np.linspace(0.0, 2.0 * np.pi, 12, endpoint=False)  # a regular 12-gon around a
+        big = np.column_stack([a[:, 0].mean() + 10.0 * np.cos(t), a[:, 1].mean() + 10.0 * np.sin(t)])
+        assert abs(oracle.clip_area(a, big) - area(a)) <= 1e-12 * area(a)
+        if ab > 0:
+            assert oracle.polygons_intersect(a, b)
