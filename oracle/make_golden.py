@@ -173,9 +173,78 @@ def golden_barycentric(ns):
     np.savez_compressed(os.path.join(OUT, "barycentric_golden.npz"), **out)
 
 
+def structured_cases():
+    """(name, source kwargs, target kwargs) of raster pairs: ascending / descending axes,
+    equidistant midpoints, explicit cell sizes, explicit non-contiguous bounds, midpoints
+    that fall exactly on source cell bounds, targets sticking out of the source."""
+    rng = np.random.default_rng(2024)
+    cases = []
+    # the reference's own fixtures a, b, c (tests/fixtures/fixture_regridder.py:94-158)
+    a = dict(x=[50.0, 100.0, 150.0], y=[150.0, 100.0, 50.0])
+    cases.append(("a_b", a, dict(x=[25.0, 75.0, 125.0, 175.0], y=[175.0, 125.0, 75.0, 25.0])))
+    cases.append(("a_c", a, dict(x=[40.0, 90.0, 140.0, 190.0], y=[175.0, 125.0, 75.0, 25.0])))
+    cases.append(("b_a", dict(x=[25.0, 75.0, 125.0, 175.0], y=[175.0, 125.0, 75.0, 25.0]), a))
+    for i in range(6):
+        nsx, nsy, ntx, nty = rng.integers(3, 30, 4)
+        sx = np.sort(rng.uniform(0, 100, 1))[0] + np.arange(nsx) * rng.uniform(1, 5)
+        sy = np.sort(rng.uniform(0, 100, 1))[0] + np.arange(nsy) * rng.uniform(1, 5)
+        tx = sx[0] - 3.0 + np.arange(ntx) * (sx[-1] - sx[0] + 6.0) / ntx
+        ty = sy[0] + 1.0 + np.arange(nty) * (sy[-1] - sy[0]) / nty
+        if i % 2:
+            sy, ty = sy[::-1], ty[::-1]
+        if i % 3 == 0:
+            sx = sx[::-1]
+        if i % 3 == 1:
+            tx = tx[::-1]
+        cases.append((f"rand{i}", dict(x=sx, y=sy), dict(x=tx, y=ty)))
+    # commensurate lattices: every other target midpoint lies exactly on a source bound
+    cases.append(("ties", dict(x=np.arange(0.5, 8.5), y=np.arange(7.5, 0.0, -1.0)),
+                  dict(x=np.arange(0.0, 9.0, 0.5), y=np.arange(8.0, -0.5, -0.5))))
+    # explicit, non-equidistant bounds (fixture e, fixture_regridder.py:160-182) and cell sizes
+    e_bounds = np.column_stack(([17.5, 42.5, 92.5], [42.5, 92.5, 117.5]))
+    cases.append(("a_e", a, dict(x=[30.0, 67.5, 105.0], y=[175.0, 125.0, 75.0, 25.0], xkw=dict(bounds=e_bounds))))
+    edges = np.cumsum(np.r_[0.0, rng.uniform(0.5, 3.0, 12)])
+    cases.append(("nonequi", dict(x=0.5 * (edges[1:] + edges[:-1]), y=np.arange(10.0, 0.0, -1.0),
+                                  xkw=dict(bounds=np.column_stack((edges[:-1], edges[1:])))),
+                  dict(x=np.linspace(1.0, 20.0, 17), y=np.linspace(9.7, 0.2, 23))))
+    return cases
+
+
+def golden_structured():
+    st = ref_loader.load_structured()
+    out = {}
+    names = []
+    for name, s_kw, t_kw in structured_cases():
+        src, tgt = st.grid(**s_kw), st.grid(**t_kw)
+        names.append(name)
+        for key, kw in (("s", s_kw), ("t", t_kw)):
+            out[f"{name}_{key}x"], out[f"{name}_{key}y"] = np.asarray(kw["x"], float), np.asarray(kw["y"], float)
+            for ax in ("x", "y"):
+                b = (kw.get(ax + "kw") or {}).get("bounds")
+                if b is not None:
+                    out[f"{name}_{key}{ax}bounds"] = np.asarray(b, float)
+        results = {
+            "overlap": src.overlap(tgt, relative=False),
+            "relative": src.overlap(tgt, relative=True),
+            "centroid": src.locate_centroids(tgt, None),
+        }
+        try:
+            results["linear"] = src.linear_weights(tgt)
+        except ValueError:
+            pass
+        for kind, (si, ti, w) in results.items():
+            order = np.lexsort((w, si, ti))
+            out[f"{name}_{kind}_source"], out[f"{name}_{kind}_target"] = si[order], ti[order]
+            out[f"{name}_{kind}_weight"] = w[order]
+        print("structured", name, {k: len(v[2]) for k, v in results.items()})
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "structured_golden.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
+    golden_structured()
     golden_apply(ns)
     golden_coo(ns)
     golden_connectivity(ns)

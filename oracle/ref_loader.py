@@ -107,3 +107,60 @@ def load():
     ns.replace_interpolated_weights = ext.replace_interpolated_weights
     _cache["ns"] = ns
     return ns
+
+
+def load_structured():
+    """The reference's separable raster path (xugrid/regrid/structured.py,
+    overlap_1d.py, utils.py).  structured.py imports xarray, UnstructuredGrid2d and
+    Ugrid2d at module level but its 1-D / 2-D weight methods only touch numpy
+    attributes, so those three imports are stubbed and grids are assembled with
+    ``axis()`` / ``grid()`` below instead of the xarray-reading constructors
+    (structured.py:33-83 is restated in ``axis``: same midpoints / bounds /
+    flipped / side)."""
+    if "st" in _cache:
+        return _cache["st"]
+    import numpy as np
+
+    load()
+    if "xarray" not in sys.modules:
+        xr = types.ModuleType("xarray")
+        xr.DataArray = type("DataArray", (), {})
+        xr.Dataset = type("Dataset", (), {})
+        sys.modules["xarray"] = xr
+    if "xugrid.regrid.unstructured" not in sys.modules:
+        un = types.ModuleType("xugrid.regrid.unstructured")
+        un.UnstructuredGrid2d = type("UnstructuredGrid2d", (), {})
+        sys.modules["xugrid.regrid.unstructured"] = un
+    if "xugrid.ugrid.ugrid2d" not in sys.modules:
+        ug = types.ModuleType("xugrid.ugrid.ugrid2d")
+        ug.Ugrid2d = type("Ugrid2d", (), {})
+        sys.modules["xugrid.ugrid.ugrid2d"] = ug
+    _load("xugrid.regrid.utils", "xugrid/regrid/utils.py")
+    _load("xugrid.regrid.overlap_1d", "xugrid/regrid/overlap_1d.py")
+    st = _load("xugrid.regrid.structured", "xugrid/regrid/structured.py")
+
+    def axis(index, name, bounds=None, size=None):
+        g = object.__new__(st.StructuredGrid1d)
+        index = np.asarray(index, dtype=float)
+        if index.size > 1 and (np.diff(index) < 0).all():
+            mid, flipped, side = index[::-1], True, "right"
+        else:
+            mid, flipped, side = index, False, "left"
+        if bounds is None:
+            if size is None:
+                size = np.full_like(mid, np.diff(mid)[0])
+            a = np.abs(np.broadcast_to(np.asarray(size, dtype=float), mid.shape))
+            bounds = np.column_stack((mid - 0.5 * a, mid + 0.5 * a))
+        g.name, g.midpoints, g.bounds = name, mid, np.asarray(bounds, dtype=float)
+        g.flipped, g.side, g.index = flipped, side, index
+        return g
+
+    def grid(x, y, xkw=None, ykw=None):
+        g = object.__new__(st.StructuredGrid2d)
+        g.xbounds = axis(x, "x", **(xkw or {}))
+        g.ybounds = axis(y, "y", **(ykw or {}))
+        return g
+
+    ns = types.SimpleNamespace(module=st, axis=axis, grid=grid)
+    _cache["st"] = ns
+    return ns

@@ -122,3 +122,44 @@ def hexagon_mesh(nx=6, ny=5, seed=0):
     # append triangles (fill -1)
     tri = np.array([[0, 1, 2, -1, -1, -1], [6, 7, 9, -1, -1, -1]], dtype=np.int64)
     return verts, np.vstack([faces, tri])
+
+
+# ---- structured fixtures a..e of /root/reference/tests/fixtures/fixture_regridder.py:94-182 -----
+# (midpoints; dx = 50 / dy = -50 unless stated) and the expectations the reference holds for them
+FIX_A = dict(x=[50.0, 100.0, 150.0], y=[150.0, 100.0, 50.0])
+FIX_B = dict(x=[25.0, 75.0, 125.0, 175.0], y=[175.0, 125.0, 75.0, 25.0])
+FIX_C = dict(x=[40.0, 90.0, 140.0, 190.0], y=[175.0, 125.0, 75.0, 25.0])
+FIX_E_X = [30.0, 67.5, 105.0]
+FIX_E_XBOUNDS = np.column_stack(([17.5, 42.5, 92.5], [42.5, 92.5, 117.5]))
+FIX_A_DATA = np.arange(9.0).reshape(3, 3)                       # fixture_regridder.py:94-105
+FIX_A_LAYERED = np.arange(18.0).reshape(2, 3, 3)                # :108-121
+
+# tests/test_regrid/test_structured.py:108-205: 36 (source, target) pairs, every weight 625.0
+OVERLAP_2D_SOURCE = np.repeat(np.arange(9), 4)
+OVERLAP_2D_TARGET = np.array([0, 4, 5, 1, 2, 6, 5, 1, 2, 3, 7, 6, 8, 9, 5, 4, 9, 5, 10, 6, 10, 11, 7, 6,
+                              9, 8, 12, 13, 10, 14, 13, 9, 10, 11, 14, 15])
+# test_structured.py:249-262
+CENTROID_2D_SOURCE = np.array([0, 1, 3, 4])
+CENTROID_2D_TARGET = np.array([5, 6, 9, 10])
+# test_structured.py:51-105: the 1-D cases (source, target, length)
+OVERLAP_1D = {
+    "a_b": ([0, 0, 1, 1, 2, 2], [0, 1, 1, 2, 2, 3], [25.0] * 6),
+    "a_b_flipped": ([0, 0, 1, 1, 2, 2], [2, 3, 1, 2, 0, 1], [25.0] * 6),
+    "a_e": ([0, 0, 1, 1], [0, 1, 1, 2], [17.5, 32.5, 17.5, 25.0]),
+    "a_e_relative": ([0, 0, 1, 1], [0, 1, 1, 2], [17.5 / 50.0, 32.5 / 50.0, 17.5 / 50.0, 25.0 / 50.0]),
+}
+# fixture_regridder.py:240-362 (consumed by test_regridder.py:100-150 with a weak `.any()`;
+# asserted as full equality here)
+EXPECTED_CENTROID = np.array([nan, nan, nan, nan, nan, 0, 1, nan, nan, 3, 4, nan, nan, nan, nan, nan]).reshape(4, 4)
+EXPECTED_OVERLAP = np.array([0.0, 0.5, 1.5, 2.0, 1.5, 2.0, 3.0, 3.5, 4.5, 5.0, 6.0, 6.5, 6.0, 6.5, 7.5, 8.0]).reshape(4, 4)
+EXPECTED_LINEAR = np.array([nan, nan, nan, nan, nan, 2.0, 3.0, nan, nan, 5.0, 6.0, nan, nan, nan, nan, nan]).reshape(4, 4)
+
+
+def strip_axis_y():
+    """one row of unit height: a 1-D grid as a strip of quads (areas == lengths)"""
+    return dict(y=[0.5], ybounds=np.array([[0.0, 1.0]]))
+
+
+def pair_set(source, target, weight):
+    """the comparison of test_structured.py:29-48: the set of (target, source) pairs with weights"""
+    return sorted(zip(np.asarray(target).tolist(), np.asarray(source).tolist(), np.asarray(weight, float).tolist()))

@@ -99,9 +99,13 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+def ptr(t: Optional[torch.Tensor], dtype: Optional[torch.dtype] = None) -> Optional[int]:
+    """Raw device pointer of a contiguous CUDA tensor; with ``dtype`` the element type
+    is checked too (the library reinterprets the bytes it is handed)."""
     if t is None:
         return None
     if not t.is_cuda or not t.is_contiguous():
         raise XgError("expected a contiguous CUDA tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise XgError(f"expected a {dtype} tensor, received {t.dtype}")
     return t.data_ptr()

@@ -158,14 +158,20 @@ class CellTree2d:
                     ctypes.byref(job),
                 )
             )
-            st = (ctypes.c_int64 * 8)()
-            _native.check(L.xg_overlap_stats(job, st))
-            self.last_stats = OverlapStats(*[int(st[i]) for i in range(7)])
-            ms = (ctypes.c_double * 8)()
-            _native.check(L.xg_overlap_timings(job, ms))
-            self.last_phase_ms = dict(zip(PHASES, [float(ms[i]) for i in range(len(PHASES))]))
-            indices = torch.empty(nnz.value, dtype=torch.int32, device=self.device)
-            area = torch.empty(nnz.value, dtype=torch.float64, device=self.device)
+            try:
+                st = (ctypes.c_int64 * 8)()
+                _native.check(L.xg_overlap_stats(job, st))
+                self.last_stats = OverlapStats(*[int(st[i]) for i in range(7)])
+                ms = (ctypes.c_double * 8)()
+                _native.check(L.xg_overlap_timings(job, ms))
+                self.last_phase_ms = dict(zip(PHASES, [float(ms[i]) for i in range(len(PHASES))]))
+                indices = torch.empty(nnz.value, dtype=torch.int32, device=self.device)
+                area = torch.empty(nnz.value, dtype=torch.float64, device=self.device)
+            except BaseException:
+                # the job holds the pair / survivor / provisional arenas (several GB at 10 M
+                # faces) and is only released by xg_overlap_finish: do not leak it
+                L.xg_overlap_abort(job)
+                raise
             _native.check(
                 L.xg_overlap_finish(
                     job, _native.ptr(indptr), _native.ptr(indices), _native.ptr(area),

@@ -365,13 +365,6 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
     double2 *bufA = s_buf + threadIdx.x;
     double2 *bufB = s_buf + (size_t)M * BT + threadIdx.x;
     double2 *stg = s_buf + (size_t)2 * M * BT + threadIdx.x;
-#ifdef XG_REC_PREFETCH
-    // UNVALIDATED tuning build (profiles/r1_pending_record_prefetch.md): the survivor record
-    // two trips ahead travels by cp.async into one of two per-thread slots, because ptxas
-    // sinks the plain load to its first use (17 % of the kernel's stall samples)
-    int2 *rec = reinterpret_cast<int2 *>(s_buf + (size_t)3 * M * BT) + threadIdx.x;
-    int rslot = 0;
-#endif
     const unsigned long long stride = (unsigned long long)gridDim.x * BT;
     unsigned long long q = (unsigned long long)blockIdx.x * BT + threadIdx.x;
 
@@ -398,11 +391,7 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
         if (KT > 3) na = tnv[r.x] & 0x7f;
         if (KS > 3) nb = snv[r.y] & 0x7f;
     }
-#ifdef XG_REC_PREFETCH
-    if (q + stride < n_surv) cp_async8(rec, surv + q + stride);
-#else
     if (q + stride < n_surv) r_next = surv[q + stride];
-#endif
     int2 pend_r = make_int2(-1, 0);  // x < 0: nothing pending
     int64_t pend_base = 0;
     double pend_ar = 0.0;
@@ -420,22 +409,13 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
         const int na_cur = na, nb_cur = nb;
         // ---- prefetch
         if (q + stride < n_surv) {
-#ifdef XG_REC_PREFETCH
-            r = rec[rslot * BT];
-#else
             r = r_next;
-#endif
             stage(r);
             base = ld_i64_here(prov_ptr + r.x);
             if (KT > 3) na = tnv[r.x] & 0x7f;
             if (KS > 3) nb = snv[r.y] & 0x7f;
         }
-#ifdef XG_REC_PREFETCH
-        if (q + 2 * stride < n_surv) cp_async8(rec + (rslot ^ 1) * BT, surv + q + 2 * stride);
-        rslot ^= 1;
-#else
         if (q + 2 * stride < n_surv) r_next = ld_int2_here(surv + q + 2 * stride);
-#endif
         schedule_fence();
         // ---- clip
         double ar;
@@ -723,9 +703,6 @@ static int launch_clip(const ClipArgs &A, cudaStream_t s) {
     XG_CHECK_LAUNCH();
     if (A.between) XG_CUDA(cudaEventRecord(A.between, s));
     size_t smem = sizeof(double2) * 3 * (size_t)(KT + KS) * BT;  // 2 ping-pong lists + 1 staged pair
-#ifdef XG_REC_PREFETCH
-    smem += sizeof(int2) * 2 * (size_t)BT;  // + two survivor-record slots
-#endif
     auto kern = k_clip_survivors<KT, KS, BT, MINB>;
     XG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem));

@@ -281,6 +281,68 @@ class Ugrid2d:
     def compute_barycentric_weights(self, points, tolerance: Optional[float] = None):
         return self.celltree.compute_barycentric_weights(points, tolerance)
 
+    def sel_points(self, obj, x, y, method: Optional[str] = None, out_of_bounds: str = "warn",
+                   fill_value=np.nan, tolerance: Optional[float] = None) -> "PointSelection":
+        """
+        Values of face data at points (/root/reference/xugrid/ugrid/ugridbase.py:1125-1259):
+        every point is located in the mesh on the GPU (``xg_locate_points``) and the
+        data of the face that holds it is selected.  ``obj`` is a ``UgridDataArray`` or an
+        array whose LAST axis is the face dimension.  ``out_of_bounds``: "raise", "warn"
+        (warning + ``fill_value``), "ignore" (``fill_value``) or "drop" (such points are
+        left out; ``PointSelection.index`` tells which were kept).  Only containment is
+        offered: ``method="nearest"`` and data on nodes or edges need the reference's
+        KD-trees, which are not part of the regridding path.
+        """
+        import warnings
+
+        method_options = (None, "nearest")
+        if method not in method_options:
+            raise ValueError(f"method must be one of {method_options}, received: {method}")
+        bounds_options = ("warn", "raise", "ignore", "drop")
+        if out_of_bounds not in bounds_options:
+            raise ValueError(
+                f"out_of_bounds must be one of {', '.join(bounds_options)}, received: {out_of_bounds}"
+            )
+        if method == "nearest":
+            raise NotImplementedError("sel_points(method='nearest') is not part of the GPU regridding path")
+        x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+        y = np.atleast_1d(np.asarray(y, dtype=np.float64))
+        if x.shape != y.shape:
+            raise ValueError("shape of x does not match shape of y")
+        if x.ndim != 1:
+            raise ValueError("x and y must be 1d")
+        data = obj.data if isinstance(obj, UgridDataArray) else obj
+        if data.shape[-1] != self.n_face:
+            raise ValueError(
+                f"last axis of obj must be the face dimension ({self.n_face}), received shape {tuple(data.shape)}"
+            )
+        xy = np.column_stack([x, y])
+        index = self.locate_points(xy, tolerance)
+        valid = index != -1
+        keep = np.arange(x.size)
+        if not valid.all():
+            msg = "Not all points are located on the topology."
+            if out_of_bounds == "raise":
+                raise ValueError(msg)
+            if out_of_bounds == "warn":
+                warnings.warn(msg, UserWarning, stacklevel=2)
+            if out_of_bounds == "drop":
+                keep = keep[valid]
+                index, valid = index[valid], valid[valid]
+        is_tensor = isinstance(data, torch.Tensor)
+        if is_tensor:
+            take = torch.from_numpy(np.where(valid, index, 0)).to(data.device)
+            values = data.index_select(data.dim() - 1, take)
+            if not valid.all():
+                values = values.to(torch.result_type(values, torch.tensor(fill_value)))
+                values[..., torch.from_numpy(~valid).to(data.device)] = fill_value
+        else:
+            values = np.asarray(data)[..., np.where(valid, index, 0)]
+            if not valid.all():
+                values = values.astype(np.result_type(values.dtype, np.asarray(fill_value).dtype))
+                values[..., ~valid] = fill_value
+        return PointSelection(values, xy[keep, 0], xy[keep, 1], keep, f"{self.name}_points")
+
     def rasterize_like(self, x, y):
         # ugrid2d.py:1080-1101
         x = np.asarray(x, dtype=np.float64)
@@ -334,6 +396,20 @@ class Ugrid2d:
         y = bounds1d_to_vertices(y_bounds)
         node_y, node_x = (a.ravel() for a in np.meshgrid(y, x, indexing="ij"))
         return Ugrid2d._from_intervals_helper(node_x, node_y, nx, ny, name)
+
+
+class PointSelection:
+    """Result of ``Ugrid2d.sel_points``: ``values`` (last axis = the selected points,
+    dimension ``<mesh>_points``), their coordinates (the reference attaches them as
+    ``<mesh>_x`` / ``<mesh>_y``) and ``index`` = positions of the kept points in the
+    caller's x / y."""
+
+    def __init__(self, values, x, y, index, dim: str):
+        self.values, self.x, self.y, self.index, self.dim = values, x, y, index, dim
+
+    def __array__(self, dtype=None, copy=None):
+        v = self.values.cpu().numpy() if isinstance(self.values, torch.Tensor) else np.asarray(self.values)
+        return v.astype(dtype) if dtype is not None else v
 
 
 class Ugrid1d:
@@ -455,6 +531,11 @@ class StructuredAxis:
         return len(self.bounds)
 
     @property
+    def length(self) -> np.ndarray:
+        # structured.py:106-108
+        return np.abs(self.bounds[:, 1] - self.bounds[:, 0])
+
+    @property
     def directional_bounds(self) -> np.ndarray:
         return self.bounds[::-1, :].copy() if self.flipped else self.bounds
 
@@ -485,6 +566,11 @@ class StructuredGrid2d:
     @property
     def coords(self) -> dict:
         return {self.ybounds.name: self.ybounds.index, self.xbounds.name: self.xbounds.index}
+
+    @property
+    def area(self) -> np.ndarray:
+        # structured.py:485-487
+        return np.multiply.outer(self.ybounds.length, self.xbounds.length)
 
     def to_ugrid2d(self) -> Ugrid2d:
         # structured.py:489-501

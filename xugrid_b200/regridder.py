@@ -27,7 +27,7 @@ from typing import Callable, Optional, Tuple, Union
 import numpy as np
 import torch
 
-from . import sparse
+from . import _native, sparse
 from .grid import StructuredGrid2d, Ugrid1d, Ugrid2d, UgridDataArray
 from .sparse import MatrixCOO, MatrixCSR
 
@@ -277,6 +277,17 @@ def _target_points(target, device) -> torch.Tensor:
     return target.ugrid_topology.centroids_device
 
 
+def _both_structured(source, target) -> bool:
+    return isinstance(source, _StructuredAdapter) and isinstance(target, _StructuredAdapter)
+
+
+def _csr_rows(A: MatrixCSR, begin: int, end: int) -> MatrixCSR:
+    """rows [begin, end) of a CSR matrix (the shard of a rank that owns a target range)"""
+    lo, hi = int(A.indptr[begin].item()), int(A.indptr[end].item())
+    return MatrixCSR(A.data[lo:hi].contiguous(), A.indices[lo:hi].contiguous(),
+                     (A.indptr[begin:end + 1] - lo).contiguous(), end - begin, A.m, hi - lo)
+
+
 def setup_grid(obj):
     # regridder.py:72-80
     if isinstance(obj, (Ugrid2d, UgridDataArray)):
@@ -321,6 +332,12 @@ class BaseRegridder(abc.ABC):
         self._target = setup_grid(target)
         self._weights = None
         self._target_range = target_range
+        if _both_structured(self._source, self._target):
+            # raster -> raster: the separable path of the reference (convert_to_match,
+            # regridder.py:83-96); no mesh, no spatial index, nothing to upload
+            _native.lib()  # the weights are applied on the GPU: no CPU fallback
+            self._compute_weights(self._source, self._target, tolerance)
+            return
         # start both uploads on the copy stream: the index build over the source
         # overlaps with the transfer of the target
         src_grid = self._source.to_unstructured().ugrid_topology
@@ -426,6 +443,13 @@ class BaseRegridder(abc.ABC):
         w = self._weights
         if w is None:
             raise ValueError("Weights have not been computed yet.")
+        if self._target_range is not None:
+            # the rows of one shard next to the topology of the whole target would read back
+            # as a mis-shaped regridder: collect the rows of all ranks first
+            raise ValueError(
+                "this regridder holds only the target rows [{}, {}); call gather_weights() "
+                "before exporting the weights".format(*self._target_range)
+            )
         ds = {}
         if isinstance(w, MatrixCSR):
             data, indices, indptr = w.to_numpy()
@@ -467,8 +491,20 @@ class BaseRegridder(abc.ABC):
     def _weights_from_dataset(cls, ds: dict):
         return cls._csr_from_dataset(ds)
 
+    def to_xarray(self):
+        """``to_dataset()`` as an ``xarray.Dataset`` in the reference's layout
+        (needs xarray; see xugrid_b200/xarray_io.py)."""
+        from . import xarray_io
+
+        return xarray_io.to_xarray(self.to_dataset())
+
     @classmethod
-    def from_weights(cls, weights: dict, target):
+    def from_weights(cls, weights, target):
+        if not isinstance(weights, dict):
+            # an xarray.Dataset as written by the reference's to_dataset()
+            from . import xarray_io
+
+            weights = xarray_io.from_xarray(weights)
         instance = cls.__new__(cls)
         instance._weights = cls._weights_from_dataset(weights)
         instance._target = setup_grid(target)
@@ -477,7 +513,11 @@ class BaseRegridder(abc.ABC):
         return instance
 
     @classmethod
-    def from_dataset(cls, dataset: dict):
+    def from_dataset(cls, dataset):
+        if not isinstance(dataset, dict):
+            from . import xarray_io
+
+            dataset = xarray_io.from_xarray(dataset)
         target = _grid_from_dataset(dataset, "__target")
         return cls.from_weights(dataset, target)
 
@@ -490,6 +530,12 @@ class CentroidLocatorRegridder(BaseRegridder):
     def _compute_weights(self, source, target, tolerance=None):
         if self._target_range is not None:
             raise NotImplementedError("target_range is only supported by the overlap regridders")
+        if _both_structured(source, target):
+            # structured.py:549-574
+            from . import structured
+
+            self._weights = structured.locate_centroids(source.grid, target.grid)
+            return
         # (a raster target is only needed as points: it is not promoted to a quad mesh)
         source_index, target_index, weight_values = source.to_unstructured().locate_centroids(target, tolerance)
         self._weights = MatrixCOO(weight_values, target_index.contiguous(), source_index.contiguous(),
@@ -517,6 +563,13 @@ class BaseOverlapRegridder(BaseRegridder, abc.ABC):
 
     def _overlap_weights(self, source, target, relative: bool) -> None:
         # regridder.py:428-436
+        if _both_structured(source, target):
+            # structured.py:523-547
+            from . import structured
+
+            A = structured.overlap(source.grid, target.grid, relative)
+            self._weights = A if self._target_range is None else _csr_rows(A, *self._target_range)
+            return
         src, tgt = source.to_unstructured(), target.to_unstructured()
         self._weights = src.overlap(tgt, relative=relative, target_range=self._target_range)
 
@@ -572,8 +625,9 @@ class BarycentricInterpolator(BaseRegridder):
     """
     regridder.py:589-659.  Interpolates between the values of the source faces
     (located at their centroids) with barycentric weights inside the Voronoi
-    polygons around the source nodes.  A structured source is treated as a quad
-    mesh (the reference's separable ``linear_weights`` path is out of scope).
+    polygons around the source nodes.  Raster -> raster takes the reference's
+    separable ``linear_weights`` path (xugrid_b200/structured.py); a raster source
+    with a mesh target is promoted to a quad mesh, as in the reference.
     """
 
     _METHODS = ("mean",)
@@ -587,6 +641,12 @@ class BarycentricInterpolator(BaseRegridder):
     def _compute_weights(self, source, target, tolerance=None):
         if self._target_range is not None:
             raise NotImplementedError("target_range is only supported by the overlap regridders")
+        if _both_structured(source, target):
+            # regridder.py:629-631 -> structured.py:576-601 (bilinear between cell centres)
+            from . import structured
+
+            self._weights = structured.linear_weights(source.grid, target.grid)
+            return
         # (a raster target is only needed as points: it is not promoted to a quad mesh)
         self._weights = source.to_unstructured().barycentric(target, tolerance)
 

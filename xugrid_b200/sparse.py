@@ -31,10 +31,14 @@ class MatrixCOO(NamedTuple):
         row = to_device(row, torch.int32, dev)
         col = to_device(col, torch.int32, dev)
         data = to_device(data, torch.float64, dev)
+        if row.shape != col.shape or row.shape != data.shape or row.dim() != 1:
+            raise ValueError("row, col and data must be 1D arrays of equal length")
         if n is None:
-            n = int(row.max().item()) + 1
+            n = int(row.max().item()) + 1 if row.numel() else 0
         if m is None:
-            m = int(col.max().item()) + 1
+            m = int(col.max().item()) + 1 if col.numel() else 0
+        _check_index_range(row, int(n), "row")
+        _check_index_range(col, int(m), "col")
         return MatrixCOO(data, row, col, int(n), int(m), int(data.numel()))
 
     def to_csr(self) -> "MatrixCSR":
@@ -71,6 +75,18 @@ class MatrixCSR(NamedTuple):
         data = to_device(data, torch.float64, dev)
         indices = to_device(indices, torch.int32, dev)
         indptr = to_device(indptr, torch.int64, dev)
+        # a stale or mismatched weights file must raise here, as the reference's numpy
+        # indexing would (IndexError), instead of sending the kernels out of bounds
+        if indptr.dim() != 1 or indptr.numel() != int(n) + 1:
+            raise ValueError(f"indptr must have n + 1 = {int(n) + 1} entries, received {tuple(indptr.shape)}")
+        if indices.shape != data.shape or data.dim() != 1:
+            raise ValueError("indices and data must be 1D arrays of equal length")
+        first, last = (int(v) for v in indptr[[0, -1]].tolist())
+        if first != 0 or last != data.numel():
+            raise ValueError(f"indptr must run from 0 to nnz = {data.numel()}, received {first} .. {last}")
+        if indptr.numel() > 1 and bool((indptr[1:] < indptr[:-1]).any().item()):
+            raise ValueError("indptr must be non-decreasing")
+        _check_index_range(indices, int(m), "indices")
         return MatrixCSR(data, indices, indptr, int(n), int(m), int(data.numel()))
 
     def to_coo(self) -> MatrixCOO:
@@ -87,6 +103,28 @@ class MatrixCSR(NamedTuple):
             self.indices.to(torch.int64).cpu().numpy(),
             self.indptr.cpu().numpy(),
         )
+
+
+def _check_index_range(index: torch.Tensor, size: int, name: str) -> None:
+    """0 <= index < size (one min/max pass on the device)."""
+    if index.numel() == 0:
+        return
+    lo, hi = (int(v) for v in torch.aminmax(index))
+    if lo < 0 or hi >= size:
+        raise IndexError(f"{name} out of range: values {lo} .. {hi} for size {size}")
+
+
+def _check_source(source: torch.Tensor, A, what: str) -> None:
+    """The library reads ``source`` as (n_extra, m) float64 on the device of the
+    weights: anything else would be reinterpreted bytes or an out-of-bounds gather."""
+    if source.dim() != 2:
+        raise ValueError("source must be (n_extra, m)")
+    if source.dtype != torch.float64:
+        raise _native.XgError(f"{what}: source must be float64, received {source.dtype}")
+    if source.device != A.data.device:
+        raise _native.XgError(f"{what}: source is on {source.device}, the weights on {A.data.device}")
+    if int(source.shape[1]) != A.m:
+        raise ValueError(f"source has {int(source.shape[1])} columns, weights expect {A.m}")
 
 
 def _dev(device, like) -> torch.device:
@@ -131,21 +169,23 @@ def csr_apply(
     the target (a shard built with t_begin/t_end) when they are given.
     """
     L = _native.lib()
-    if source.dim() != 2:
-        raise ValueError("source must be (n_extra, m)")
+    _check_source(source, A, "csr_apply")
     n_extra, m = int(source.shape[0]), int(source.shape[1])
-    if m != A.m:
-        raise ValueError(f"source has {m} columns, weights expect {A.m}")
     rows = A.n if row_end is None else row_end - row_begin
+    if rows != A.indptr.numel() - 1:
+        raise ValueError(f"indptr describes {A.indptr.numel() - 1} rows, {rows} requested")
     if out is None:
         out = torch.empty((n_extra, rows), dtype=torch.float64, device=source.device)
-    if not out.is_cuda or out.dtype != torch.float64 or (rows > 1 and out.stride(1) != 1):
-        raise _native.XgError("out must be a float64 CUDA tensor with unit stride along the rows")
+    if (not out.is_cuda or out.dtype != torch.float64 or out.device != source.device
+            or (rows > 1 and out.stride(1) != 1) or out.shape[0] < n_extra or out.shape[1] < rows):
+        raise _native.XgError("out must be a float64 CUDA tensor of at least (n_extra, rows) on the "
+                              "device of the source, with unit stride along the rows")
     with torch.cuda.device(source.device):
         _native.check(
             L.xg_csr_apply(
-                code, float(percentile), _native.ptr(A.indptr), _native.ptr(A.indices),
-                _native.ptr(A.data), _native.ptr(source), n_extra, m, rows, out.data_ptr(),
+                code, float(percentile), _native.ptr(A.indptr, torch.int64), _native.ptr(A.indices, torch.int32),
+                _native.ptr(A.data, torch.float64), _native.ptr(source.contiguous(), torch.float64), n_extra, m,
+                rows, out.data_ptr(),
                 int(out.stride(0)) if n_extra > 1 else max(rows, int(out.stride(0))),
                 _native.stream_ptr(),
             )
@@ -156,12 +196,16 @@ def csr_apply(
 def coo_gather(source: torch.Tensor, A: MatrixCOO, size: int) -> torch.Tensor:
     """``CentroidLocatorRegridder._regrid`` (regridder.py:400-409) on the device."""
     L = _native.lib()
+    _check_source(source, A, "coo_gather")
+    if size < A.n:
+        raise ValueError(f"size {size} is smaller than the {A.n} rows of the weights")
     n_extra, m = int(source.shape[0]), int(source.shape[1])
     out = torch.empty((n_extra, size), dtype=torch.float64, device=source.device)
     with torch.cuda.device(source.device):
         _native.check(
             L.xg_coo_gather(
-                _native.ptr(A.row), _native.ptr(A.col), A.nnz, _native.ptr(source), n_extra, m,
+                _native.ptr(A.row, torch.int32), _native.ptr(A.col, torch.int32), A.nnz,
+                _native.ptr(source.contiguous(), torch.float64), n_extra, m,
                 _native.ptr(out), size, _native.stream_ptr(),
             )
         )
