@@ -11,9 +11,12 @@
  *    of the last failure on the calling thread is xg_last_error_string().
  *    Nothing throws, nothing falls back to the CPU.
  *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it.
- *    Functions that must return a size to the host (xg_overlap_begin,
- *    xg_index_create) synchronise that stream before returning; all others
- *    are asynchronous.
+ *    Functions that must return a size to the host synchronise that stream
+ *    before returning: xg_overlap_begin (nnz), the culled index builds (number
+ *    of faces kept), xg_intersect_edges (count), xg_face_range_bounds;
+ *    xg_index_info waits for the index the first time the default tolerance
+ *    is asked for.  Everything else, including xg_index_create and
+ *    xg_index_destroy, is asynchronous.
  *  - connectivity is (n_face, k) row-major with -1 as fill value and 0-based
  *    node indices (what xugrid's Ugrid2d normalises to:
  *    /root/reference/xugrid/ugrid/ugrid2d.py:103-109), as int32 or int64
@@ -88,6 +91,14 @@ int xg_index_create(const double *d_xy, int64_t n_node, const void *d_faces, int
 int xg_index_create_clipped(const double *d_xy, int64_t n_node, const void *d_faces, int idx_bytes,
                             int64_t n_face, int k, const double *h_clip_box, void *stream,
                             xg_index **out);
+/* Same cull, but the box is the bounding box of the target faces [t_begin, t_end) of
+ * another mesh, reduced on the device: nothing about the targets travels to the host, so a
+ * rank's sharded build costs one host round trip less than xg_face_range_bounds +
+ * xg_index_create_clipped. */
+int xg_index_create_for_targets(const double *d_xy, int64_t n_node, const void *d_faces, int idx_bytes,
+                                int64_t n_face, int k, const double *d_t_xy, const void *d_t_faces,
+                                int t_idx_bytes, int64_t t_begin, int64_t t_end, int k_t, void *stream,
+                                xg_index **out);
 /* h_box = [xmin, xmax, ymin, ymax] of the vertices of faces [f_begin, f_end):
  * the clip box of a target shard (synchronises the stream). */
 int xg_face_range_bounds(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,

@@ -422,3 +422,20 @@ def test_network_gridder_reference_known_answers(xb, structured):
     assert np.array_equal(np.asarray(again.regrid(data)), out, equal_nan=True)
     with pytest.raises(TypeError):
         xb.NetworkGridder(raster.to_ugrid2d(), target)
+
+
+def test_target_range_of_the_point_regridders(xb, disk):
+    """CentroidLocatorRegridder / BarycentricInterpolator built for a range of target faces
+    give exactly the columns of the full regridder (rows are independent)."""
+    txy, tf = synthetic.jittered_lattice(23, 19, 61, "mixed", bounds=(-9.0, 9.0, -9.0, 9.0))
+    target = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf)
+    raster = quads(xb, 0.5)
+    values = np.stack([disk.values, disk.values[::-1]])
+    for cls in (xb.CentroidLocatorRegridder, xb.BarycentricInterpolator):
+        for tgt in (target, raster):
+            full = cls(disk, tgt).regrid(values).reshape(2, -1)
+            n = full.shape[1]
+            for b, e in ((0, n // 3), (n // 3, n), (5, 5)):
+                part = cls(disk, tgt, target_range=(b, e)).regrid(values)
+                assert part.shape == (2, e - b)
+                assert np.array_equal(part, full[:, b:e], equal_nan=True), (cls.__name__, b, e)

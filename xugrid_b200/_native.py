@@ -31,6 +31,8 @@ SIGNATURES = {
     "xg_index_create": (_int, [_vp, _i64, _vp, _int, _i64, _int, _vp, ctypes.POINTER(_vp)]),
     "xg_index_create_clipped": (_int, [_vp, _i64, _vp, _int, _i64, _int, ctypes.POINTER(_dbl), _vp,
                                        ctypes.POINTER(_vp)]),
+    "xg_index_create_for_targets": (_int, [_vp, _i64, _vp, _int, _i64, _int, _vp, _vp, _int, _i64, _i64, _int, _vp,
+                                           ctypes.POINTER(_vp)]),
     "xg_face_range_bounds": (_int, [_vp, _vp, _int, _i64, _i64, _int, ctypes.POINTER(_dbl), _vp]),
     "xg_index_destroy": (_int, [_vp]),
     "xg_index_info": (_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_dbl)]),

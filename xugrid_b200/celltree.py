@@ -84,9 +84,12 @@ class OverlapStats(NamedTuple):
 
 class CellTree2d:
     def __init__(self, vertices: ArrayLike, faces: ArrayLike, fill_value: int = -1, device=None,
-                 clip_box=None):
+                 clip_box=None, clip_targets=None):
         """``clip_box=(xmin, xmax, ymin, ymax)`` indexes only the faces whose bounding
-        box meets the box (used by ranks that own a range of target faces)."""
+        box meets the box (used by ranks that own a range of target faces);
+        ``clip_targets=(xy, faces, begin, end)`` (device tensors of another mesh) takes
+        the box from the bounds of those target faces, reduced on the device -- no
+        host round trip."""
         L = _native.lib()
         self.device = _device(device)
         with torch.cuda.device(self.device):
@@ -97,24 +100,59 @@ class CellTree2d:
             self.n_face, self.k = int(self.faces.shape[0]), int(self.faces.shape[1])
             self.n_node = int(self.vertices.shape[0])
             h = ctypes.c_void_p()
-            box = None if clip_box is None else (ctypes.c_double * 4)(*[float(v) for v in clip_box])
-            _native.check(
-                L.xg_index_create_clipped(
-                    _native.ptr(self.vertices), self.n_node, _native.ptr(self.faces),
-                    self.faces.element_size(), self.n_face, self.k, box, _native.stream_ptr(),
-                    ctypes.byref(h),
+            if clip_targets is not None:
+                t_xy, t_faces, t_begin, t_end = clip_targets
+                _native.check(
+                    L.xg_index_create_for_targets(
+                        _native.ptr(self.vertices), self.n_node, _native.ptr(self.faces),
+                        self.faces.element_size(), self.n_face, self.k, _native.ptr(t_xy, torch.float64),
+                        _native.ptr(t_faces), t_faces.element_size(), int(t_begin), int(t_end),
+                        int(t_faces.shape[1]), _native.stream_ptr(), ctypes.byref(h),
+                    )
                 )
-            )
+            else:
+                box = None if clip_box is None else (ctypes.c_double * 4)(*[float(v) for v in clip_box])
+                _native.check(
+                    L.xg_index_create_clipped(
+                        _native.ptr(self.vertices), self.n_node, _native.ptr(self.faces),
+                        self.faces.element_size(), self.n_face, self.k, box, _native.stream_ptr(),
+                        ctypes.byref(h),
+                    )
+                )
         self._h = h
-        info = (ctypes.c_int64 * 8)()
-        tol = ctypes.c_double()
-        _native.check(L.xg_index_info(self._h, info, ctypes.byref(tol)))
-        self.n_indexed = int(info[0])
-        self.n_levels = int(info[2])
-        self.device_bytes = int(info[3])
-        self.default_tolerance = float(tol.value)
+        self._info = None
+        self._tolerance = None
         self.last_stats: Optional[OverlapStats] = None
         self.last_phase_ms: dict = {}
+
+    # sizes are known when the build has been enqueued; the default tolerance is reduced on
+    # the device and only waited for when somebody asks (an overlap job never does)
+    def _index_info(self):
+        if self._info is None:
+            info = (ctypes.c_int64 * 8)()
+            _native.check(_native.load_library().xg_index_info(self._h, info, None))
+            self._info = [int(v) for v in info]
+        return self._info
+
+    @property
+    def n_indexed(self) -> int:
+        return self._index_info()[0]
+
+    @property
+    def n_levels(self) -> int:
+        return self._index_info()[2]
+
+    @property
+    def device_bytes(self) -> int:
+        return self._index_info()[3]
+
+    @property
+    def default_tolerance(self) -> float:
+        if self._tolerance is None:
+            tol = ctypes.c_double()
+            _native.check(_native.load_library().xg_index_info(self._h, None, ctypes.byref(tol)))
+            self._tolerance = float(tol.value)
+        return self._tolerance
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -103,6 +103,51 @@ static void release_cache() {
     g_cached_bytes = 0;
 }
 
+// ---- pinned host slots (128 bytes each) for asynchronous read-backs ---------------------------
+static std::mutex g_pin_mutex;
+static std::vector<double *> g_pin_free;
+
+double *pinned_slot_acquire() {
+    std::lock_guard<std::mutex> lock(g_pin_mutex);
+    if (g_pin_free.empty()) {
+        void *block = nullptr;
+        const int slots = 64;
+        if (cudaHostAlloc(&block, 128 * slots, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        for (int i = 0; i < slots; ++i) g_pin_free.push_back(reinterpret_cast<double *>((char *)block + 128 * i));
+    }
+    double *p = g_pin_free.back();
+    g_pin_free.pop_back();
+    return p;
+}
+
+void pinned_slot_release(double *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pin_mutex);
+    g_pin_free.push_back(p);
+}
+
+int index_host_values(const xg_index *cix) {
+    xg_index *ix = const_cast<xg_index *>(cix);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (ix->host_values_valid) return XG_OK;
+    if (ix->frame_ready) XG_CUDA(cudaEventSynchronize(ix->frame_ready));
+    if (ix->h_frame) {
+        for (int i = 0; i < 4; ++i) ix->bounds[i] = ix->h_frame[i];
+        ix->default_tolerance = ix->h_frame[4];
+    }
+    ix->host_values_valid = true;
+    return XG_OK;
+}
+
+void index_note_use(const xg_index *cix, cudaStream_t s) {
+    xg_index *ix = const_cast<xg_index *>(cix);
+    if (s == ix->arena_stream) return;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    for (cudaStream_t f : ix->foreign_streams)
+        if (f == s) return;
+    ix->foreign_streams.push_back(s);
+}
+
 // ---- kernels ------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long order_bits(double v) {
     unsigned long long u = (unsigned long long)__double_as_longlong(v);
@@ -154,27 +199,15 @@ __global__ void k_frame_from_red(const unsigned long long *red, double *frame) {
     frame[4] = sqrt(__longlong_as_double((long long)red[4])) * 1e-12;  // default tolerance
 }
 
-__device__ __forceinline__ uint32_t spread16(uint32_t v) {
-    v &= 0xffffu;
-    v = (v | (v << 8)) & 0x00ff00ffu;
-    v = (v | (v << 4)) & 0x0f0f0f0fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
-    return v;
-}
-
-// optional cull: faces whose bbox does not strictly intersect the box get the
-// key 0xFFFFFFFF (sorted to the end, never packed); kept faces are counted
-struct ClipBox {
-    double xmin, xmax, ymin, ymax;
-    int on;
-};
+// optional cull: only faces whose bbox strictly intersects the clip box (device memory:
+// [xmin, xmax, ymin, ymax], e.g. the bounds of a rank's target range reduced on the
+// device a moment ago) are kept, appended compactly and counted
 
 template <typename I, int KMAX>
 __global__ void __launch_bounds__(256)
 k_face_keys(const double2 *__restrict__ xy, const I *__restrict__ faces, int64_t f_begin,
             int64_t n, int k, const double *__restrict__ frame, uint32_t *__restrict__ keys,
-            int32_t *__restrict__ ids, unsigned long long *diag2_max, const ClipBox clip,
+            int32_t *__restrict__ ids, unsigned long long *diag2_max, const double *__restrict__ clip,
             unsigned long long *__restrict__ kept) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     double d2 = 0.0;
@@ -193,27 +226,27 @@ k_face_keys(const double2 *__restrict__ xy, const I *__restrict__ faces, int64_t
             xmin = fmin(xmin, p.x); xmax = fmax(xmax, p.x);
             ymin = fmin(ymin, p.y); ymax = fmax(ymax, p.y);
         }
-        const double fx0 = frame[0], fx1 = frame[1], fy0 = frame[2], fy1 = frame[3];
-        const double cx = 0.5 * (xmin + xmax), cy = 0.5 * (ymin + ymax);
-        const double sx = fx1 > fx0 ? 65536.0 / (fx1 - fx0) : 0.0;
-        const double sy = fy1 > fy0 ? 65536.0 / (fy1 - fy0) : 0.0;
-        double qx = (cx - fx0) * sx, qy = (cy - fy0) * sy;
-        qx = fmin(fmax(qx, 0.0), 65534.0);  // 0xFFFFFFFF stays free for culled faces
-        qy = fmin(fmax(qy, 0.0), 65534.0);
-        uint32_t key = spread16((uint32_t)qx) | (spread16((uint32_t)qy) << 1);
-        if (clip.on) {
-            in_box = xmin < clip.xmax && clip.xmin < xmax && ymin < clip.ymax && clip.ymin < ymax;
-            if (!in_box) key = 0xFFFFFFFFu;
+        // a culled build looks at every face of the mesh but keeps few (1/8 on 8 ranks):
+        // key and diagonal only for the kept ones
+        in_box = !clip || (xmin < clip[1] && clip[0] < xmax && ymin < clip[3] && clip[2] < ymax);
+        if (in_box) {
+            const double fx0 = frame[0], fx1 = frame[1], fy0 = frame[2], fy1 = frame[3];
+            const double cx = 0.5 * (xmin + xmax), cy = 0.5 * (ymin + ymax);
+            const double sx = fx1 > fx0 ? 65536.0 / (fx1 - fx0) : 0.0;
+            const double sy = fy1 > fy0 ? 65536.0 / (fy1 - fy0) : 0.0;
+            double qx = (cx - fx0) * sx, qy = (cy - fy0) * sy;
+            qx = fmin(fmax(qx, 0.0), 65534.0);
+            qy = fmin(fmax(qy, 0.0), 65534.0);
+            my_key = curve_key16((uint32_t)qx, (uint32_t)qy);
+            if (!clip) {
+                keys[i] = my_key;
+                ids[i] = (int32_t)(f_begin + i);
+            }
+            const double dx = xmax - xmin, dy = ymax - ymin;
+            d2 = dx * dx + dy * dy;
         }
-        if (!clip.on) {
-            keys[i] = key;
-            ids[i] = (int32_t)(f_begin + i);
-        }
-        my_key = key;
-        const double dx = xmax - xmin, dy = ymax - ymin;
-        d2 = dx * dx + dy * dy;
     }
-    if (clip.on) {
+    if (clip) {
         // culled build: kept faces are appended compactly (one atomic per warp)
         const unsigned m = __ballot_sync(0xffffffffu, in_box);
         if (m) {
@@ -376,7 +409,7 @@ k_reduce_level(const Box *__restrict__ child, int64_t n_child, Box *__restrict__
 template <typename I>
 static int launch_face_keys(const double2 *xy, const I *faces, int64_t f_begin, int64_t n, int k,
                             const double *frame, uint32_t *keys, int32_t *ids,
-                            unsigned long long *diag2, const ClipBox &clip, unsigned long long *kept,
+                            unsigned long long *diag2, const double *clip, unsigned long long *kept,
                             cudaStream_t s) {
     if (n == 0) return XG_OK;
     const int B = 256;
@@ -404,30 +437,31 @@ static int launch_pack(const double2 *xy, const I *faces, int k, const int32_t *
 }
 
 static void ensure_pool_config() {
-    static bool done = false;
-    if (done) return;
+    // once per device (a process may drive several), under a lock
+    static std::mutex mu;
+    static std::vector<int> configured;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int d : configured)
+        if (d == dev) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;  // keep freed blocks cached: repeated builds reuse them
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    done = true;
+    configured.push_back(dev);
 }
 
 int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
               int64_t f_end, int k, const double *d_frame, unsigned long long *d_diag2,
-              PackedMesh *out, cudaStream_t s, const double *h_clip_box, unsigned long long *d_kept) {
+              PackedMesh *out, cudaStream_t s, const double *d_clip_box, unsigned long long *d_kept) {
     ensure_pool_config();
     const int64_t n = f_end - f_begin;
     out->n = n;
     out->k = k;
-    ClipBox clip;
-    clip.on = (h_clip_box && d_kept) ? 1 : 0;
-    clip.xmin = clip.on ? h_clip_box[0] : 0.0; clip.xmax = clip.on ? h_clip_box[1] : 0.0;
-    clip.ymin = clip.on ? h_clip_box[2] : 0.0; clip.ymax = clip.on ? h_clip_box[3] : 0.0;
-    if (clip.on) XG_CUDA(cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), s));
+    const double *clip = (d_clip_box && d_kept) ? d_clip_box : nullptr;
+    if (clip) XG_CUDA(cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), s));
     const double2 *xy = reinterpret_cast<const double2 *>(d_xy);
     DevBuf keys_in, keys_out, ids_in, tmp;
     XG_CUDA(keys_in.alloc(sizeof(uint32_t) * (size_t)n, s));
@@ -442,10 +476,16 @@ int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_
                                        keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, clip, d_kept, s);
     if (rc) return rc;
     int64_t n_pack = n;
-    if (clip.on) {
+    if (clip) {
+        // the one host round trip of a culled build: the sort below is sized on the host
+        double *slot = pinned_slot_acquire();
+        if (!slot) { set_error("pack_mesh: no pinned host memory"); return XG_ERR_NOMEM; }
+        cudaError_t e = cudaMemcpyAsync(slot, d_kept, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         unsigned long long h_kept = 0;
-        XG_CUDA(cudaMemcpyAsync(&h_kept, d_kept, sizeof(h_kept), cudaMemcpyDeviceToHost, s));
-        XG_CUDA(cudaStreamSynchronize(s));
+        memcpy(&h_kept, slot, sizeof(h_kept));
+        pinned_slot_release(slot);
+        if (e != cudaSuccess) return cuda_fail(e, "kept count", __FILE__, __LINE__);
         n_pack = (int64_t)h_kept;
         out->n = n_pack;
     }
@@ -483,15 +523,33 @@ extern "C" const char *xg_last_error_string(void) { return xg::g_err; }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-extern "C" int xg_index_create(const double *d_xy, int64_t n_node, const void *d_faces,
-                               int idx_bytes, int64_t n_face, int k, void *stream,
-                               xg_index **out) {
-    return xg_index_create_clipped(d_xy, n_node, d_faces, idx_bytes, n_face, k, nullptr, stream, out);
+// a range of target faces whose bounds cull the source mesh (xg_index_create_for_targets)
+struct TargetRange {
+    const double *d_xy;
+    const void *d_faces;
+    int idx_bytes;
+    int64_t begin, end;
+    int k;
+};
+
+static int launch_range_bounds(const TargetRange &t, unsigned long long *d_red, cudaStream_t s) {
+    const int64_t n = t.end - t.begin;
+    if (n <= 0) return XG_OK;
+    if (t.idx_bytes == 4)
+        k_face_range_bounds<int32_t><<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)t.d_xy, (const int32_t *)t.d_faces,
+                                                               t.begin, n, t.k, d_red);
+    else
+        k_face_range_bounds<int64_t><<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)t.d_xy, (const int64_t *)t.d_faces,
+                                                               t.begin, n, t.k, d_red);
+    XG_CHECK_LAUNCH();
+    return XG_OK;
 }
 
-extern "C" int xg_index_create_clipped(const double *d_xy, int64_t n_node, const void *d_faces,
-                                       int idx_bytes, int64_t n_face, int k,
-                                       const double *h_clip_box, void *stream, xg_index **out) {
+// h_clip_box (host) or targets (bounds reduced on the device, no host round trip) restrict
+// the index to the source faces whose bbox strictly meets the box; both NULL: all faces
+static int index_create_impl(const double *d_xy, int64_t n_node, const void *d_faces, int idx_bytes,
+                             int64_t n_face, int k, const double *h_clip_box, const TargetRange *targets,
+                             void *stream, xg_index **out) {
     if (!out) { set_error("xg_index_create: out is NULL"); return XG_ERR_INVALID; }
     *out = nullptr;
     if (n_face < 0 || n_node < 0 || (idx_bytes != 4 && idx_bytes != 8) ||
@@ -511,6 +569,7 @@ extern "C" int xg_index_create_clipped(const double *d_xy, int64_t n_node, const
     ensure_pool_config();
     xg_index *ix = new xg_index();
     ix->n_face = n_face; ix->n_node = n_node; ix->k = k;
+    const bool culled = h_clip_box || targets;
 
     // level sizes
     int64_t level_n[MAX_LEVELS];
@@ -523,7 +582,8 @@ extern "C" int xg_index_create_clipped(const double *d_xy, int64_t n_node, const
     }
     ix->n_levels = n_levels;
 
-    // one arena: boxes | level boxes | poly | perm | nvert | frame(8 doubles) | red(8 u64)
+    // one arena: boxes | level boxes | poly | perm | nvert | frame(8 doubles) | red(8 u64) |
+    //            clip box(4 doubles) + its reduction cells(8 u64)
     size_t off = 0;
     const size_t off_box = off; off = align_up(off + sizeof(Box) * (size_t)n_face, 256);
     size_t off_lvl[MAX_LEVELS];
@@ -536,6 +596,8 @@ extern "C" int xg_index_create_clipped(const double *d_xy, int64_t n_node, const
     const size_t off_nv = off; off = align_up(off + (size_t)n_face, 256);
     const size_t off_frame = off; off = align_up(off + sizeof(double) * 8, 256);
     const size_t off_red = off; off = align_up(off + sizeof(unsigned long long) * 8, 256);
+    const size_t off_clip = off; off = align_up(off + sizeof(double) * 8, 256);
+    const size_t off_clip_red = off; off = align_up(off + sizeof(unsigned long long) * 8, 256);
     ix->bytes = off;
     ix->arena_stream = s;
     cudaError_t e = scratch_alloc(&ix->arena, &ix->arena_cap, off, s);
@@ -549,6 +611,8 @@ extern "C" int xg_index_create_clipped(const double *d_xy, int64_t n_node, const
     double *d_frame = (double *)(base + off_frame);
     ix->d_frame = d_frame;
     unsigned long long *d_red = (unsigned long long *)(base + off_red);
+    double *d_clip = (double *)(base + off_clip);
+    unsigned long long *d_clip_red = (unsigned long long *)(base + off_clip_red);
 
     int rc = XG_OK;
     do {
@@ -557,12 +621,22 @@ extern "C" int xg_index_create_clipped(const double *d_xy, int64_t n_node, const
             k_node_bounds<<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)d_xy, n_node, d_red);
         k_frame_from_red<<<1, 1, 0, s>>>(d_red, d_frame);
         if (cudaGetLastError() != cudaSuccess) { rc = XG_ERR_CUDA; set_error("index: launch failed"); break; }
+        if (h_clip_box) {
+            // (a pageable source is staged by the runtime before the call returns)
+            e = cudaMemcpyAsync(d_clip, h_clip_box, sizeof(double) * 4, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "clip box upload", __FILE__, __LINE__); break; }
+        } else if (targets) {
+            k_init_red<<<1, 1, 0, s>>>(d_clip_red);
+            rc = launch_range_bounds(*targets, d_clip_red, s);
+            if (rc) break;
+            k_frame_from_red<<<1, 1, 0, s>>>(d_clip_red, d_clip);
+        }
         PackedMesh pm;
         pm.perm = ix->perm; pm.box = ix->leaf_box; pm.poly = ix->poly; pm.nvert = ix->nvert;
-        rc = pack_mesh(d_xy, d_faces, idx_bytes, 0, n_face, k, d_frame, d_red + 4, &pm, s, h_clip_box,
-                       d_red + 5);
+        rc = pack_mesh(d_xy, d_faces, idx_bytes, 0, n_face, k, d_frame, d_red + 4, &pm, s,
+                       culled ? d_clip : nullptr, d_red + 5);
         if (rc) break;
-        if (h_clip_box) {
+        if (culled) {
             // only the faces that can meet the box are indexed
             ix->n_face = pm.n;
             n_levels = 0;
@@ -587,20 +661,51 @@ extern "C" int xg_index_create_clipped(const double *d_xy, int64_t n_node, const
             n_child = np;
         }
         if (cudaGetLastError() != cudaSuccess) { rc = XG_ERR_CUDA; set_error("index: launch failed"); break; }
-        double h[5];
-        e = cudaMemcpyAsync(h, d_frame, sizeof(h), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        // bounds + default tolerance travel to a pinned host slot behind the build; nobody
+        // waits for them here (index_host_values does, the first time they are asked for)
+        ix->h_frame = pinned_slot_acquire();
+        if (!ix->h_frame) { rc = XG_ERR_NOMEM; set_error("index: no pinned host memory"); break; }
+        e = cudaMemcpyAsync(ix->h_frame, d_frame, sizeof(double) * 5, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->frame_ready, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(ix->frame_ready, s);
         if (e != cudaSuccess) { rc = cuda_fail(e, "index finalize", __FILE__, __LINE__); break; }
-        ix->bounds[0] = h[0]; ix->bounds[1] = h[1]; ix->bounds[2] = h[2]; ix->bounds[3] = h[3];
-        ix->default_tolerance = h[4];
     } while (0);
     if (rc) {
+        if (ix->frame_ready) cudaEventDestroy(ix->frame_ready);
+        pinned_slot_release(ix->h_frame);
         scratch_free(ix->arena, ix->arena_cap, s);
         delete ix;
         return rc;
     }
     *out = ix;
     return XG_OK;
+}
+
+extern "C" int xg_index_create(const double *d_xy, int64_t n_node, const void *d_faces,
+                               int idx_bytes, int64_t n_face, int k, void *stream,
+                               xg_index **out) {
+    return index_create_impl(d_xy, n_node, d_faces, idx_bytes, n_face, k, nullptr, nullptr, stream, out);
+}
+
+extern "C" int xg_index_create_clipped(const double *d_xy, int64_t n_node, const void *d_faces,
+                                       int idx_bytes, int64_t n_face, int k,
+                                       const double *h_clip_box, void *stream, xg_index **out) {
+    return index_create_impl(d_xy, n_node, d_faces, idx_bytes, n_face, k, h_clip_box, nullptr, stream, out);
+}
+
+extern "C" int xg_index_create_for_targets(const double *d_xy, int64_t n_node, const void *d_faces,
+                                           int idx_bytes, int64_t n_face, int k, const double *d_t_xy,
+                                           const void *d_t_faces, int t_idx_bytes, int64_t t_begin,
+                                           int64_t t_end, int k_t, void *stream, xg_index **out) {
+    if (!d_t_xy || !d_t_faces || t_begin < 0 || t_end < t_begin || k_t < 3 ||
+        (t_idx_bytes != 4 && t_idx_bytes != 8)) {
+        set_error("xg_index_create_for_targets: invalid target range");
+        return XG_ERR_INVALID;
+    }
+    TargetRange tr;
+    tr.d_xy = d_t_xy; tr.d_faces = d_t_faces; tr.idx_bytes = t_idx_bytes;
+    tr.begin = t_begin; tr.end = t_end; tr.k = k_t;
+    return index_create_impl(d_xy, n_node, d_faces, idx_bytes, n_face, k, nullptr, &tr, stream, out);
 }
 
 extern "C" int xg_face_range_bounds(const double *d_xy, const void *d_faces, int idx_bytes,
@@ -634,10 +739,26 @@ extern "C" int xg_face_range_bounds(const double *d_xy, const void *d_faces, int
 extern "C" int xg_index_destroy(xg_index *ix) {
     if (!ix) return XG_OK;
     if (ix->arena) {
-        // queries may have been enqueued on other streams than the creation stream
-        cudaDeviceSynchronize();
+        // queries may have been enqueued on other streams than the creation stream: the
+        // arena goes back to the block cache of the creation stream, ordered behind the
+        // work of those streams by events (no device-wide synchronisation)
+        for (cudaStream_t f : ix->foreign_streams) {
+            cudaEvent_t ev;
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventRecord(ev, f) != cudaSuccess ||
+                cudaStreamWaitEvent(ix->arena_stream, ev, 0) != cudaSuccess) {
+                cudaDeviceSynchronize();  // (cannot order it: fall back to the big hammer)
+            }
+            cudaEventDestroy(ev);
+        }
         scratch_free(ix->arena, ix->arena_cap, ix->arena_stream);
     }
+    if (ix->frame_ready) {
+        // the pinned slot must not be handed out again while the copy into it is in flight
+        cudaEventSynchronize(ix->frame_ready);
+        cudaEventDestroy(ix->frame_ready);
+    }
+    pinned_slot_release(ix->h_frame);
     delete ix;
     return XG_OK;
 }
@@ -650,6 +771,10 @@ extern "C" int xg_release_cached_memory(void) {
 
 extern "C" int xg_index_info(const xg_index *ix, int64_t info[8], double *tol) {
     if (!ix) { set_error("xg_index_info: NULL index"); return XG_ERR_INVALID; }
+    if (tol) {
+        const int rc = index_host_values(ix);
+        if (rc) return rc;
+    }
     if (info) {
         info[0] = ix->n_face; info[1] = ix->k; info[2] = ix->n_levels; info[3] = (int64_t)ix->bytes;
         info[4] = ix->n_node; info[5] = info[6] = info[7] = 0;

@@ -29,15 +29,6 @@ struct LocateParams {
     int top;
 };
 
-__device__ __forceinline__ uint32_t spread16p(uint32_t v) {
-    v &= 0xffffu;
-    v = (v | (v << 8)) & 0x00ff00ffu;
-    v = (v | (v << 4)) & 0x0f0f0f0fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
-    return v;
-}
-
 __global__ void __launch_bounds__(256)
 k_point_keys(const double2 *__restrict__ pts, int64_t n, const double *__restrict__ frame,
              uint32_t *__restrict__ keys, int32_t *__restrict__ ids) {
@@ -51,7 +42,7 @@ k_point_keys(const double2 *__restrict__ pts, int64_t n, const double *__restric
     // NaN-safe clamp: fmax(NaN, 0) = 0
     qx = fmin(fmax(qx, 0.0), 65535.0);
     qy = fmin(fmax(qy, 0.0), 65535.0);
-    keys[i] = spread16p((uint32_t)qx) | (spread16p((uint32_t)qy) << 1);
+    keys[i] = curve_key16((uint32_t)qx, (uint32_t)qy);
     ids[i] = (int32_t)i;
 }
 
@@ -184,7 +175,7 @@ k_edge_keys(const double4 *__restrict__ edges, int64_t n, const double *__restri
     double qx = (0.5 * (e.x + e.z) - fx0) * sx, qy = (0.5 * (e.y + e.w) - fy0) * sy;
     qx = fmin(fmax(qx, 0.0), 65535.0);
     qy = fmin(fmax(qy, 0.0), 65535.0);
-    keys[i] = spread16p((uint32_t)qx) | (spread16p((uint32_t)qy) << 1);
+    keys[i] = curve_key16((uint32_t)qx, (uint32_t)qy);
     ids[i] = (int32_t)i;
 }
 
@@ -345,7 +336,9 @@ extern "C" int xg_locate_points(const xg_index *index, const double *d_points, i
         return XG_ERR_INVALID;
     }
     if (n_point >= (int64_t)1 << 31) { set_error("xg_locate_points: more than 2^31 points"); return XG_ERR_UNSUPPORTED; }
+    if (tolerance < 0) { const int rc = index_host_values(index); if (rc) return rc; }
     const double tol = tolerance < 0 ? index->default_tolerance : tolerance;
+    index_note_use(index, (cudaStream_t)stream);
     return locate_impl(index, d_points, n_point, tol, d_face_index, nullptr, (cudaStream_t)stream);
 }
 
@@ -359,7 +352,9 @@ extern "C" int xg_barycentric(const xg_index *index, const double *d_points, int
     if (n_point >= (int64_t)1 << 31) { set_error("xg_barycentric: more than 2^31 points"); return XG_ERR_UNSUPPORTED; }
     if (n_point == 0) return XG_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if (tolerance < 0) { const int rc = index_host_values(index); if (rc) return rc; }
     const double tol = tolerance < 0 ? index->default_tolerance : tolerance;
+    index_note_use(index, s);
     DevBuf pos;
     XG_CUDA(pos.alloc(sizeof(int32_t) * (size_t)n_point, s));
     int rc = locate_impl(index, d_points, n_point, tol, d_face_index, pos.as<int32_t>(), s);
@@ -383,6 +378,7 @@ extern "C" int xg_intersect_edges(const xg_index *index, const double *d_edges, 
     *h_count = 0;
     if (n_edge == 0 || index->n_face == 0) return XG_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    index_note_use(index, s);
     const int64_t n = n_edge;
     DevBuf keys_in, keys_out, ids_in, order, tmp, counter;
     XG_CUDA(keys_in.alloc(sizeof(uint32_t) * (size_t)n, s));

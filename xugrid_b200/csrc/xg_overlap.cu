@@ -39,12 +39,13 @@ namespace xg {
 
 constexpr int TRAV_WARPS = 8;
 constexpr int TRAV_STACK = 256;
-#ifndef XG_TRAV_U
-#define XG_TRAV_U 3
+#ifndef XG_TRAV_PREFETCH
+#define XG_TRAV_PREFETCH 1
 #endif
-constexpr int TRAV_U = XG_TRAV_U;               // children tested per leaf trip
-constexpr int TRAV_QFLUSH = 64;                 // flush threshold
-constexpr int TRAV_QCAP = TRAV_QFLUSH + 32 * TRAV_U;  // pair queue entries per warp (one trip adds <= 32 * TRAV_U)
+#ifndef XG_TRAV_QCAP
+#define XG_TRAV_QCAP 192
+#endif
+constexpr int TRAV_QCAP = XG_TRAV_QCAP;         // pair queue entries per warp; flushed when the next node's pairs do not fit
 constexpr int PAIRS_PER_TARGET_GUESS = 16;
 
 // device counters of one job
@@ -89,6 +90,12 @@ __device__ __forceinline__ int64_t ld_i64_here(const int64_t *p) {
     return (int64_t)v;
 }
 __device__ __forceinline__ void schedule_fence() { asm volatile("" ::: "memory"); }
+__device__ __forceinline__ Box ld_box_here(const Box *p) {
+    Box b;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];\n" : "=d"(b.xmin), "=d"(b.xmax) : "l"(p));
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2+16];\n" : "=d"(b.ymin), "=d"(b.ymax) : "l"(p));
+    return b;
+}
 
 // pairs[i] = {sorted target position, sorted source position}
 __global__ void __launch_bounds__(TRAV_WARPS * 32)
@@ -99,7 +106,6 @@ k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t, in
     __shared__ int32_t s_stack[TRAV_WARPS][TRAV_STACK];
     __shared__ int2 s_q[TRAV_WARPS][TRAV_QCAP];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
     // tile_stride > 1: density sampling pass (every tile_stride-th tile, cap == 0: count only)
     const int64_t tile = (blockIdx.x * (int64_t)TRAV_WARPS + w) * tile_stride;
     const int64_t t = tile * 32 + lane;
@@ -132,20 +138,39 @@ k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t, in
         qn = 0;
     };
 
-    __syncwarp();
-    while (sp > 0) {
-        const int32_t entry = s_stack[w][--sp];
+    // The walk is a chain of dependent node loads (pop -> load 32 child boxes -> test -> push),
+    // and since the per-lane hit masks took the instruction count down it is bound by that
+    // latency, not by issue slots: the boxes of the NEXT stack entry are requested before the
+    // current node is processed.  (The order of the walk changes -- the entry below the top
+    // is visited before the children the current node pushes -- which no result depends on.)
+    auto load_node = [&](int32_t entry) {
         const int d = entry >> 27;
         const int64_t c0 = (int64_t)(entry & 0x7ffffff) * FANOUT;
-        const Box *cb = P.boxes[d - 1];
         const int64_t nc = P.count[d - 1] - c0;
-        Box mine;
-        if (lane < nc) mine = cb[c0 + lane];
-        else { mine.xmin = INFINITY; mine.xmax = -INFINITY; mine.ymin = INFINITY; mine.ymax = -INFINITY; }
+        Box b;
+        b.xmin = INFINITY; b.xmax = -INFINITY; b.ymin = INFINITY; b.ymax = -INFINITY;
+        if (lane < nc) b = ld_box_here(P.boxes[d - 1] + c0 + lane);
+        return b;
+    };
+    __syncwarp();
+    int32_t entry = s_stack[w][--sp];
+    Box mine = load_node(entry);
+    while (true) {
+#if XG_TRAV_PREFETCH
+        int32_t entry_next = -1;
+        Box mine_next;
+        if (sp > 0) {
+            entry_next = s_stack[w][--sp];
+            mine_next = load_node(entry_next);
+        }
+        schedule_fence();
+#endif
+        const int d = entry >> 27;
+        const int64_t c0 = (int64_t)(entry & 0x7ffffff) * FANOUT;
         ++visits;
         unsigned m = __ballot_sync(0xffffffffu, boxes_intersect(mine, ub));
         __syncwarp();
-        if (m == 0) continue;
+        if (m != 0) {
         s_node[w][lane] = mine;
         __syncwarp();
         if (d > 1) {
@@ -160,36 +185,69 @@ k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t, in
             }
         } else {
             tests += __popc(m);
-            // TRAV_U children per trip: all boxes are loaded before any is tested
+            // every lane collects the children that meet ITS target as a bit mask (two
+            // children per trip: both boxes are loaded before either is tested); nothing
+            // is voted or queued per child
+            unsigned hits = 0u;
             while (m) {
-                int c[TRAV_U];
-                bool on[TRAV_U];
+                const int ca = __ffs(m) - 1;
+                m &= m - 1;
+                const bool two = m != 0u;
+                const int cb2 = two ? __ffs(m) - 1 : ca;
+                m &= m - 1;
+                const Box ba = s_node[w][ca], bb = s_node[w][cb2];
+                const bool ha = boxes_intersect(tb, ba), hb = two & boxes_intersect(tb, bb);
+                hits |= (ha ? 1u : 0u) << ca;
+                hits |= (hb ? 1u : 0u) << cb2;
+            }
+            const int n_mine = __popc(hits);
+            my_cand += n_mine;
+            int incl = n_mine;  // inclusive prefix sum over the lanes
 #pragma unroll
-                for (int u = 0; u < TRAV_U; ++u) {
-                    on[u] = m != 0u;
-                    c[u] = on[u] ? __ffs(m) - 1 : 0;
-                    m &= m - 1;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                incl += lane >= o ? v : 0;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total > 0) {
+                if (qn > 0 && qn + total > TRAV_QCAP) flush();
+                if (total <= TRAV_QCAP) {
+                    // a lane appends its own pairs: the queue (and so the arena) holds the
+                    // pairs of a node grouped by target
+                    int pos = qn + incl - n_mine;
+                    while (hits) {
+                        const int c = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        s_q[w][pos++] = make_int2((int32_t)t, (int32_t)(c0 + c));
+                    }
+                    qn += total;
+                } else {
+                    // more pairs from one node than the queue holds (targets much larger
+                    // than the source faces): straight to the arena
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(ctr + CTR_PAIRS, (unsigned long long)total);
+                    base = __shfl_sync(0xffffffffu, base, 0) + (unsigned long long)(incl - n_mine);
+                    while (hits) {
+                        const int c = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        if (base < cap) pairs[base] = make_int2((int32_t)t, (int32_t)(c0 + c));
+                        ++base;
+                    }
                 }
-                Box bx[TRAV_U];
-#pragma unroll
-                for (int u = 0; u < TRAV_U; ++u) bx[u] = s_node[w][c[u]];
-                unsigned hm[TRAV_U];
-                bool hit[TRAV_U];
-#pragma unroll
-                for (int u = 0; u < TRAV_U; ++u) {
-                    hit[u] = on[u] & boxes_intersect(tb, bx[u]);
-                    hm[u] = __ballot_sync(0xffffffffu, hit[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < TRAV_U; ++u) {
-                    if (hit[u]) s_q[w][qn + __popc(hm[u] & lt_mask)] = make_int2((int32_t)t, (int32_t)(c0 + c[u]));
-                    my_cand += hit[u] ? 1 : 0;
-                    qn += __popc(hm[u]);
-                }
-                if (qn >= TRAV_QFLUSH) flush();
             }
         }
+        }
         __syncwarp();
+#if XG_TRAV_PREFETCH
+        if (entry_next >= 0) {
+            entry = entry_next;
+            mine = mine_next;
+            continue;
+        }
+#endif
+        if (sp == 0) break;
+        entry = s_stack[w][--sp];
+        mine = load_node(entry);
     }
     if (qn > 0) flush();
     if (valid && cand_cnt) cand_cnt[t] = my_cand;
@@ -261,7 +319,6 @@ k_sat(const int2 *__restrict__ pairs, unsigned long long cap, const double2 *__r
     // rows were sized for all of them -- nothing downstream may run; the job is re-run
     // with the exact capacity the walk counted
     if (n_pairs > cap) return;
-    const unsigned long long stride = (unsigned long long)gridDim.x * BT;
 
     auto stage = [&](const int2 r) {
         const double2 *tp = tpoly + (int64_t)r.x * kt;
@@ -510,6 +567,10 @@ struct RowMove {
     const int32_t *fill_cnt;   // (n_t) entries per provisional row
     const int32_t *prov_col;   // SORTED source position per entry
     const double *prov_val;    // overlap area per entry
+    __device__ __forceinline__ void entry(int64_t i, int32_t &col, double &val) const {
+        col = prov_col[i];
+        val = prov_val[i];
+    }
     const int32_t *tperm;      // sorted target position -> caller's target face
     int64_t t_begin;
     const int32_t *sperm;      // sorted source position -> caller's source face
@@ -536,9 +597,11 @@ __device__ __forceinline__ void move_row_regs(const RowMove &R, int64_t src, int
         k[i] = 0x7fffffff;
         v[i] = 0.0;
         if (i < n) {
-            const int32_t s = R.prov_col[src + i];
+            int32_t s;
+            double a;
+            R.entry(src + i, s, a);
             k[i] = R.sperm[s];
-            v[i] = entry_value(R, s, R.prov_val[src + i]);
+            v[i] = entry_value(R, s, a);
         }
     }
     sort_network(k, v);
@@ -606,9 +669,11 @@ k_move_long_rows(const RowMove R, const int32_t *__restrict__ long_rows,
         const int64_t dst = R.indptr[R.tperm[t] - R.t_begin];
         if (n <= SORT_LONG_CAP) {
             for (int i = lane; i < n; i += 32) {
-                const int32_t s = R.prov_col[src + i];
+                int32_t s;
+                double a;
+                R.entry(src + i, s, a);
                 s_key[w][i] = R.sperm[s];
-                s_val[w][i] = entry_value(R, s, R.prov_val[src + i]);
+                s_val[w][i] = entry_value(R, s, a);
             }
             __syncwarp();
             for (int i = lane; i < n; i += 32) {
@@ -643,9 +708,11 @@ k_move_huge_rows(const RowMove R, const int32_t *__restrict__ huge_rows,
         int32_t *key = R.indices + R.indptr[R.tperm[t] - R.t_begin];
         double *val = R.data + R.indptr[R.tperm[t] - R.t_begin];
         for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const int32_t s = R.prov_col[src + i];
+            int32_t s;
+            double a;
+            R.entry(src + i, s, a);
             key[i] = R.sperm[s];
-            val[i] = entry_value(R, s, R.prov_val[src + i]);
+            val[i] = entry_value(R, s, a);
         }
         __syncthreads();
         int64_t P = 1;
@@ -800,7 +867,8 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
     const unsigned tiles = (unsigned)div_up(n_t, 32);
     XG_CUDA(job->mark());  // XG_PHASE_TRAVERSE
     k_traverse<<<(unsigned)div_up(tiles, TRAV_WARPS), TRAV_WARPS * 32, 0, s>>>(
-        P, job->tbox.as<Box>(), n_t, 1, job->pairs.as<int2>(), cap, cand_cnt, job->ctr.as<unsigned long long>());
+        P, job->tbox.as<Box>(), n_t, 1, job->pairs.as<int2>(), cap, cand_cnt,
+        job->ctr.as<unsigned long long>());
     XG_CHECK_LAUNCH();
     {
         // provisional row starts (sorted target order): a row can hold every candidate of its target
@@ -845,12 +913,22 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
         size_t tb = job->scan_tmp_bytes;
         XG_CUDA(cub::DeviceScan::ExclusiveSum(job->scan_tmp.p, tb, it, d_indptr, n_t + 1, s));
     }
+    // the one host round trip of a job: nnz sizes the caller's arrays.  Read-backs go through
+    // a pinned slot (a pageable destination would make the copies synchronous one by one)
     int64_t nnz = 0;
     unsigned long long hc[CTR_N];
-    XG_CUDA(cudaMemcpyAsync(&nnz, d_indptr + n_t, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    XG_CUDA(cudaMemcpyAsync(hc, job->ctr.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
-    XG_CUDA(job->mark());  // end
-    XG_CUDA(cudaStreamSynchronize(s));
+    {
+        double *slot = pinned_slot_acquire();
+        if (!slot) { set_error("overlap: no pinned host memory"); return XG_ERR_NOMEM; }
+        cudaError_t e = cudaMemcpyAsync(slot, d_indptr + n_t, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(slot + 1, job->ctr.p, sizeof(hc), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = job->mark();  // end
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        memcpy(&nnz, slot, sizeof(nnz));
+        memcpy(hc, slot + 1, sizeof(hc));
+        pinned_slot_release(slot);
+        if (e != cudaSuccess) return cuda_fail(e, "overlap read-back", __FILE__, __LINE__);
+    }
     *needed = hc[CTR_PAIRS];
     if (hc[CTR_PAIRS] > cap) return XG_OK;  // caller re-runs
     job->collect();
@@ -880,6 +958,7 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
     }
     if (k_t < 3 || k_t > XG_MAX_N_VERTEX) { set_error("xg_overlap_begin: unsupported k_t=%d", k_t); return XG_ERR_UNSUPPORTED; }
     cudaStream_t s = (cudaStream_t)stream;
+    index_note_use(source, s);
     const int64_t n_t = t_end - t_begin;
     xg_overlap *job = new xg_overlap();
     job->src = source; job->t_begin = t_begin; job->n_t = n_t; job->k_t = k_t; job->s = s;

@@ -1,4 +1,4 @@
-// xg_pack.cuh -- a mesh range repacked in Morton order (see xg_index.cu).
+// xg_pack.cuh -- a mesh range repacked in space-filling-curve order (see xg_index.cu).
 #pragma once
 #include "xg_common.cuh"
 
@@ -17,11 +17,12 @@ struct PackedMesh {
 
 // d_frame: device pointer to [xmin, xmax, ymin, ymax] used to quantise the
 // Morton keys; d_diag2 (optional): running max of squared bbox diagonals.
-// h_clip_box + d_kept (optional): only faces whose bbox strictly intersects the
-// box are packed (out->n becomes their count; this synchronises the stream).
+// d_clip_box (device, [xmin, xmax, ymin, ymax]) + d_kept (optional): only faces whose
+// bbox strictly intersects the box are packed (out->n becomes their count; this is the one
+// point where the stream is synchronised: the sort is sized on the host).
 int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
               int64_t f_end, int k, const double *d_frame, unsigned long long *d_diag2,
-              PackedMesh *out, cudaStream_t s, const double *h_clip_box = nullptr,
+              PackedMesh *out, cudaStream_t s, const double *d_clip_box = nullptr,
               unsigned long long *d_kept = nullptr);
 
 }  // namespace xg

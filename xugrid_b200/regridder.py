@@ -131,11 +131,10 @@ class UnstructuredGrid2d:
         if target_range is not None and (t_end - t_begin) < other.size and t_end > t_begin:
             # a shard: index only the source faces its targets can touch
             from .celltree import CellTree2d
-            from .distributed import target_range_box
 
             sxy, sfaces = self.ugrid_topology.device_arrays()
-            tree = CellTree2d(sxy, sfaces, -1, device=sxy.device,
-                              clip_box=target_range_box(xy, faces, t_begin, t_end))
+            # (the clip box = bounds of the target range is reduced on the device)
+            tree = CellTree2d(sxy, sfaces, -1, device=sxy.device, clip_targets=(xy, faces, t_begin, t_end))
         elif tree is None:
             tree = self.ugrid_topology.celltree
         self.last_tree = tree
@@ -144,17 +143,23 @@ class UnstructuredGrid2d:
         )
         return MatrixCSR(data, indices, indptr, t_end - t_begin, self.size, int(data.numel()))
 
-    def locate_centroids(self, other: "UnstructuredGrid2d", tolerance: Optional[float] = None):
-        """unstructured.py:137-144: (source_index, target_index, ones) device tensors."""
+    def locate_centroids(self, other: "UnstructuredGrid2d", tolerance: Optional[float] = None,
+                         target_range: Optional[Tuple[int, int]] = None):
+        """unstructured.py:137-144: (source_index, target_index, ones) device tensors;
+        with ``target_range`` only for those target faces (target_index counts from its start)."""
         tree = self.ugrid_topology.celltree
-        idx = tree.locate_points_device(_target_points(other, tree.device), tolerance)
+        points = _target_points(other, tree.device)
+        if target_range is not None:
+            points = points[target_range[0]:target_range[1]].contiguous()
+        idx = tree.locate_points_device(points, tolerance)
         inside = idx != -1
         source_index = idx[inside]
-        target_index = torch.arange(other.size, dtype=torch.int32, device=idx.device)[inside]
+        target_index = torch.arange(points.shape[0], dtype=torch.int32, device=idx.device)[inside]
         weights = torch.ones(source_index.numel(), dtype=torch.float64, device=idx.device)
         return source_index, target_index, weights
 
-    def barycentric(self, other: "UnstructuredGrid2d", tolerance: Optional[float] = None) -> MatrixCSR:
+    def barycentric(self, other: "UnstructuredGrid2d", tolerance: Optional[float] = None,
+                    target_range: Optional[Tuple[int, int]] = None) -> MatrixCSR:
         """
         unstructured.py:146-201 on the device: Voronoi polygons around the
         source nodes, barycentric weights of the target centroids inside them,
@@ -167,6 +172,10 @@ class UnstructuredGrid2d:
         grid = self.ugrid_topology
         xy, faces = grid.device_arrays()
         points = _target_points(other, xy.device)
+        if target_range is not None:
+            # a shard: the rows of its own target faces (the Voronoi mesh of the source is
+            # replicated, like the source mesh of the overlap regridders)
+            points = points[target_range[0]:target_range[1]].contiguous()
         topo = voronoi.voronoi_topology(faces, xy, grid.centroids_device)
         vor_tree = CellTree2d(topo.vertices, topo.faces, -1, device=xy.device)
         face_index, weights = vor_tree.compute_barycentric_weights_device(points, tolerance)
@@ -181,7 +190,7 @@ class UnstructuredGrid2d:
         torch.cumsum(counts, 0, out=indptr[1:])
         indices = source_index[keep].to(torch.int32)
         data = weights[keep]
-        return MatrixCSR(data, indices, indptr, other.size, self.size, int(data.numel()))
+        return MatrixCSR(data, indices, indptr, int(points.shape[0]), self.size, int(data.numel()))
 
     def intersection_length(self, other: "Network1d", relative: bool):
         """unstructured.py:203-215: (target face index, source edge index, length of the
@@ -528,18 +537,19 @@ class CentroidLocatorRegridder(BaseRegridder):
     _TARGET_AS_POINTS = True
 
     def _compute_weights(self, source, target, tolerance=None):
-        if self._target_range is not None:
-            raise NotImplementedError("target_range is only supported by the overlap regridders")
         if _both_structured(source, target):
             # structured.py:549-574
             from . import structured
 
+            if self._target_range is not None:
+                raise NotImplementedError("target_range is not supported for raster -> raster regridding")
             self._weights = structured.locate_centroids(source.grid, target.grid)
             return
         # (a raster target is only needed as points: it is not promoted to a quad mesh)
-        source_index, target_index, weight_values = source.to_unstructured().locate_centroids(target, tolerance)
+        source_index, target_index, weight_values = source.to_unstructured().locate_centroids(
+            target, tolerance, self._target_range)
         self._weights = MatrixCOO(weight_values, target_index.contiguous(), source_index.contiguous(),
-                                  target.size, source.size, int(weight_values.numel()))
+                                  self._rows(), source.size, int(weight_values.numel()))
 
     def _regrid(self, source, A, size):
         return sparse.coo_gather(source, A, size)
@@ -633,22 +643,22 @@ class BarycentricInterpolator(BaseRegridder):
     _METHODS = ("mean",)
     _TARGET_AS_POINTS = True
 
-    def __init__(self, source, target, tolerance: Optional[float] = None):
-        super().__init__(source, target, tolerance)
+    def __init__(self, source, target, tolerance: Optional[float] = None,
+                 target_range: Optional[Tuple[int, int]] = None):
+        super().__init__(source, target, tolerance, target_range=target_range)
         # weights of a target face sum to 1: a weighted mean also handles NaNs
         self._setup_regrid("mean")
 
     def _compute_weights(self, source, target, tolerance=None):
-        if self._target_range is not None:
-            raise NotImplementedError("target_range is only supported by the overlap regridders")
         if _both_structured(source, target):
             # regridder.py:629-631 -> structured.py:576-601 (bilinear between cell centres)
             from . import structured
 
-            self._weights = structured.linear_weights(source.grid, target.grid)
+            A = structured.linear_weights(source.grid, target.grid)
+            self._weights = A if self._target_range is None else _csr_rows(A, *self._target_range)
             return
         # (a raster target is only needed as points: it is not promoted to a quad mesh)
-        self._weights = source.to_unstructured().barycentric(target, tolerance)
+        self._weights = source.to_unstructured().barycentric(target, tolerance, self._target_range)
 
     @classmethod
     def from_weights(cls, weights: dict, target):
