@@ -244,7 +244,8 @@ def run_ours(args) -> int:
 
     import xugrid_b200 as xb
     from xugrid_b200 import sparse
-    from xugrid_b200.distributed import all_gather_columns, shard_range, sharded_upload
+    from xugrid_b200.distributed import (all_gather_by_ids, all_gather_columns, all_gather_ids, curve_shard,
+                                         shard_range, sharded_upload)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -275,7 +276,24 @@ def run_ours(args) -> int:
 
     state = {}
 
+    # "shuffled": the face numbers mean nothing in space, so the ranks share the targets by
+    # position along the space-filling curve (every step: key all targets, take this rank's
+    # patch, and scatter the gathered output back through the id lists)
+    by_curve = args.workload == "shuffled" and world > 1
+
+    def step_curve(src):
+        ids = curve_shard(src["txy"], src["tf"], rank, world)
+        all_ids, lens = all_gather_ids(ids)
+        tree = xb.CellTree2d(src["sxy"], src["sf"], device=dev, clip_target_ids=(src["txy"], src["tf"], ids))
+        indptr, indices, area = tree.intersect_faces_csr(src["txy"], src["tf"], ids=ids)
+        A = sparse.MatrixCSR(area, indices, indptr, int(ids.numel()), n_s, int(area.numel()))
+        local = sparse.csr_apply(0, 0.0, src["values"], A, int(ids.numel()))
+        state["tree"], state["A"], state["apply_in"], state["rows"] = tree, A, src["values"], int(ids.numel())
+        return all_gather_by_ids(local, all_ids, lens, n_t)
+
     def step(src, t_range=None, gather=True):
+        if by_curve and t_range is None:
+            return step_curve(src)
         tb, te = (b, e) if t_range is None else t_range
         clip = (src["txy"], src["tf"], tb, te) if (te - tb) < n_t else None
         tree = xb.CellTree2d(src["sxy"], src["sf"], device=dev, clip_targets=clip)
@@ -283,7 +301,7 @@ def run_ours(args) -> int:
         A = sparse.MatrixCSR(area, indices, indptr, te - tb, n_s, int(area.numel()))
         local = sparse.csr_apply(0, 0.0, src["values"], A, te - tb)
         full = all_gather_columns(local, n_t) if (world > 1 and gather) else local
-        state["tree"], state["A"], state["apply_in"] = tree, A, src["values"]
+        state["tree"], state["A"], state["apply_in"], state["rows"] = tree, A, src["values"], te - tb
         return full
 
     # end-to-end leg: the public API on host data.  The grids are host containers
@@ -303,6 +321,10 @@ def run_ours(args) -> int:
     if world == 1:
         h2d_bytes = sum(nbytes(t) for t in (src_grid._xy_pin, src_grid._faces_pin, tgt_grid._xy_pin,
                                             tgt_grid._faces_pin, h["values"]))
+    elif args.workload == "shuffled":
+        # per rank: 1/world of every array (all replicated over NVLink: a rank's targets are anywhere)
+        h2d_bytes = sum(nbytes(t) for t in (src_grid._xy_pin, src_grid._faces_pin, tgt_grid._xy_pin,
+                                            tgt_grid._faces_pin, h["values"])) // world
     else:
         # per rank: 1/world of the replicated arrays (assembled over NVLink) + its own target rows
         h2d_bytes = (sum(nbytes(t) for t in (src_grid._xy_pin, src_grid._faces_pin, tgt_grid._xy_pin,
@@ -315,6 +337,16 @@ def run_ours(args) -> int:
         if world == 1:
             r = xb.OverlapRegridder(src_grid, tgt_grid, method="mean")
             state["e2e_out"] = r.regrid(h["values"])  # pinned host tensor in, pinned host tensor out
+        elif by_curve:
+            tgt_grid.prefetch(sharded=True)
+            txy_d, tf_d = tgt_grid.device_arrays()
+            ids = curve_shard(txy_d, tf_d, rank, world)
+            all_ids, lens = all_gather_ids(ids)
+            r = xb.OverlapRegridder(src_grid, tgt_grid, method="mean", target_ids=ids, sharded_upload=True)
+            local = r.regrid(sharded_upload(h["values"].reshape(-1), dev).reshape(1, -1))
+            h_out.copy_(all_gather_by_ids(local, all_ids, lens, n_t), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            state["e2e_out"] = h_out
         else:
             r = xb.OverlapRegridder(src_grid, tgt_grid, method="mean", target_range=(b, e), sharded_upload=True)
             local = r.regrid(sharded_upload(h["values"].reshape(-1), dev).reshape(1, -1))
@@ -352,11 +384,11 @@ def run_ours(args) -> int:
     A = state["A"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
-        sparse.csr_apply(0, 0.0, d["values"], A, e - b)
+        sparse.csr_apply(0, 0.0, d["values"], A, state["rows"])
     torch.cuda.synchronize()
     ev0.record()
     for _ in range(10):
-        sparse.csr_apply(0, 0.0, d["values"], A, e - b)
+        sparse.csr_apply(0, 0.0, d["values"], A, state["rows"])
     ev1.record()
     torch.cuda.synchronize()
     apply_ms = ev0.elapsed_time(ev1) / 10
@@ -385,7 +417,7 @@ def run_ours(args) -> int:
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         k_t = k_s = 3
-        rows = e - b
+        rows = state["rows"]
         kernels, have_ncu = kernel_rooflines(stats, phases, rows, k_t, k_s, peak, args.n_side, world)
         dominant = max(kernels, key=lambda k_: kernels[k_]["ms"] or 0.0)
         dk = kernels[dominant]
@@ -405,7 +437,9 @@ def run_ours(args) -> int:
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config,
-            "detail": {"nnz": stats.nnz if world == 1 else None, "sharding": f"target rows [{b},{e}) on rank 0 of {world}",
+            "detail": {"nnz": stats.nnz if world == 1 else None,
+                       "sharding": (f"{rows} targets of rank 0's patch along the space-filling curve ({world} ranks)"
+                                    if by_curve else f"target rows [{b},{e}) on rank 0 of {world}"),
                        "source_faces_indexed_on_rank0": n_indexed, "cub_launches_per_step": 12},
             "e2e": {"value": n_t / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

@@ -99,6 +99,23 @@ int xg_index_create_for_targets(const double *d_xy, int64_t n_node, const void *
                                 int64_t n_face, int k, const double *d_t_xy, const void *d_t_faces,
                                 int t_idx_bytes, int64_t t_begin, int64_t t_end, int k_t, void *stream,
                                 xg_index **out);
+/* The same with the targets given as a list of face numbers (a rank's share of a
+ * partition along the space-filling curve, xg_target_shard). */
+int xg_index_create_for_target_ids(const double *d_xy, int64_t n_node, const void *d_faces, int idx_bytes,
+                                   int64_t n_face, int k, const double *d_t_xy, const void *d_t_faces,
+                                   int t_idx_bytes, const int32_t *d_t_ids, int64_t n_ids, int k_t,
+                                   void *stream, xg_index **out);
+/* Partition of the faces of a mesh over `world` ranks by position along the
+ * space-filling (Hilbert) curve, so that every rank owns a compact patch whatever the
+ * caller's face numbering means (the reference has no counterpart).  All
+ * ranks key all faces in the frame of the mesh's own nodes, count them in 65 536 bins of
+ * the leading key bits and cut the cumulative count at multiples of n_face / world: the
+ * shards are disjoint, cover every face and differ in size by at most one bin.  Writes
+ * the face numbers of shard `rank` to d_ids (capacity n_face, no particular order) and
+ * their number to *h_count (the stream is synchronised). */
+int xg_target_shard(const double *d_xy, int64_t n_node, const void *d_faces, int idx_bytes,
+                    int64_t n_face, int k, int rank, int world, int32_t *d_ids, int64_t *h_count,
+                    void *stream);
 /* h_box = [xmin, xmax, ymin, ymax] of the vertices of faces [f_begin, f_end):
  * the clip box of a target shard (synchronises the stream). */
 int xg_face_range_bounds(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
@@ -129,6 +146,12 @@ int xg_overlap_begin(const xg_index *source, const double *d_t_xy, int64_t n_t_n
                      const void *d_t_faces, int idx_bytes, int64_t n_t_face, int k_t,
                      int64_t t_begin, int64_t t_end, int64_t *d_indptr, int64_t *h_nnz,
                      void *stream, xg_overlap **job);
+/* The same for the target faces d_t_ids[0 .. n_ids) (e.g. from xg_target_shard): row i of
+ * the CSR belongs to face d_t_ids[i]. */
+int xg_overlap_begin_ids(const xg_index *source, const double *d_t_xy, int64_t n_t_node,
+                         const void *d_t_faces, int idx_bytes, int64_t n_t_face, int k_t,
+                         const int32_t *d_t_ids, int64_t n_ids, int64_t *d_indptr, int64_t *h_nnz,
+                         void *stream, xg_overlap **job);
 int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32_t *d_indices,
                       double *d_area, int relative, void *stream);
 /* counters of the job for the byte model:

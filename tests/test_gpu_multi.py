@@ -26,7 +26,8 @@ def _worker(rank, world, port, order, q):
 
     import xugrid_b200 as xb
     from xugrid_b200 import synthetic
-    from xugrid_b200.distributed import all_gather_columns, shard_range
+    from xugrid_b200.distributed import (all_gather_by_ids, all_gather_columns, all_gather_ids, curve_shard,
+                                         shard_range)
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -56,6 +57,15 @@ def _worker(rank, world, port, order, q):
             r.gather_weights()
             again = r.regrid(torch.from_numpy(values).cuda())
             ok = ok and bool(torch.equal(again.contiguous().view(torch.int64), full.view(torch.int64)))
+        # shares along the space-filling curve (compact whatever the face numbering) + scatter by ids
+        dxy, dtf = target.device_arrays()
+        ids = curve_shard(dxy, dtf, rank, world)
+        all_ids, lens = all_gather_ids(ids)
+        r = xb.OverlapRegridder(source, target, method="mean", target_ids=ids)
+        full = all_gather_by_ids(r.regrid(torch.from_numpy(values).cuda()), all_ids, lens, n_t)
+        if rank == 0:
+            alone = xb.OverlapRegridder(source, target, method="mean").regrid(torch.from_numpy(values).cuda())
+            ok = ok and bool(torch.equal(full.contiguous().view(torch.int64), alone.contiguous().view(torch.int64)))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

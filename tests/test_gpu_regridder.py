@@ -439,3 +439,50 @@ def test_target_range_of_the_point_regridders(xb, disk):
                 part = cls(disk, tgt, target_range=(b, e)).regrid(values)
                 assert part.shape == (2, e - b)
                 assert np.array_equal(part, full[:, b:e], equal_nan=True), (cls.__name__, b, e)
+
+
+def test_curve_shards_partition_the_mesh_into_compact_patches(xb):
+    """distributed.curve_shard: disjoint, complete, balanced, and compact although the
+    faces are numbered at random"""
+    from xugrid_b200.distributed import curve_shard
+
+    txy, tf = synthetic.jittered_lattice(90, 80, 71, "tri")
+    tf = np.ascontiguousarray(tf[np.random.default_rng(7).permutation(len(tf))])
+    dxy, dtf = torch.from_numpy(txy).cuda(), torch.from_numpy(tf).cuda()
+    for world in (1, 3, 8):
+        shards = [curve_shard(dxy, dtf, r, world).cpu().numpy() for r in range(world)]
+        allids = np.concatenate(shards)
+        assert np.array_equal(np.sort(allids), np.arange(len(tf)))
+        sizes = np.array([len(s) for s in shards])
+        assert sizes.max() - sizes.min() <= 0.02 * len(tf) + 64
+        if world > 1:
+            # bounding boxes of the patches: together not much more than the domain
+            area = 0.0
+            for s in shards:
+                p = txy[tf[s]].reshape(-1, 2)
+                area += (p[:, 0].max() - p[:, 0].min()) * (p[:, 1].max() - p[:, 1].min())
+            assert area < 2.0  # unit square; random numbering with range shards would give ~ world
+
+
+def test_target_ids_give_the_columns_of_the_full_regridder(xb, disk):
+    from xugrid_b200.distributed import curve_shard
+
+    txy, tf = synthetic.jittered_lattice(31, 27, 73, "mixed", bounds=(-9.0, 9.0, -9.0, 9.0))
+    tf = np.ascontiguousarray(tf[np.random.default_rng(9).permutation(len(tf))])
+    target = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf)
+    values = np.stack([disk.values, disk.values[::-1]])
+    dxy, dtf = target.device_arrays()
+    for cls in (xb.OverlapRegridder, xb.RelativeOverlapRegridder, xb.CentroidLocatorRegridder,
+                xb.BarycentricInterpolator):
+        full = cls(disk, target).regrid(values)
+        seen = np.zeros(len(tf), dtype=bool)
+        for r in range(3):
+            ids = curve_shard(dxy, dtf, r, 3)
+            part = cls(disk, target, target_ids=ids).regrid(values)
+            idn = ids.cpu().numpy()
+            assert part.shape == (2, len(idn))
+            assert np.array_equal(part, full[:, idn], equal_nan=True), (cls.__name__, r)
+            seen[idn] = True
+        assert seen.all()
+    empty = xb.OverlapRegridder(disk, target, target_ids=torch.empty(0, dtype=torch.int32, device="cuda"))
+    assert empty.regrid(values).shape == (2, 0)

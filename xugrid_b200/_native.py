@@ -33,6 +33,9 @@ SIGNATURES = {
                                        ctypes.POINTER(_vp)]),
     "xg_index_create_for_targets": (_int, [_vp, _i64, _vp, _int, _i64, _int, _vp, _vp, _int, _i64, _i64, _int, _vp,
                                            ctypes.POINTER(_vp)]),
+    "xg_index_create_for_target_ids": (_int, [_vp, _i64, _vp, _int, _i64, _int, _vp, _vp, _int, _vp, _i64, _int, _vp,
+                                              ctypes.POINTER(_vp)]),
+    "xg_target_shard": (_int, [_vp, _i64, _vp, _int, _i64, _int, _int, _int, _vp, ctypes.POINTER(_i64), _vp]),
     "xg_face_range_bounds": (_int, [_vp, _vp, _int, _i64, _i64, _int, ctypes.POINTER(_dbl), _vp]),
     "xg_index_destroy": (_int, [_vp]),
     "xg_index_info": (_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_dbl)]),
@@ -40,6 +43,10 @@ SIGNATURES = {
         _int,
         [_vp, _vp, _i64, _vp, _int, _i64, _int, _i64, _i64, _vp, ctypes.POINTER(_i64), _vp,
          ctypes.POINTER(_vp)],
+    ),
+    "xg_overlap_begin_ids": (
+        _int,
+        [_vp, _vp, _i64, _vp, _int, _i64, _int, _vp, _i64, _vp, ctypes.POINTER(_i64), _vp, ctypes.POINTER(_vp)],
     ),
     "xg_overlap_finish": (_int, [_vp, _vp, _vp, _vp, _int, _vp]),
     "xg_overlap_stats": (_int, [_vp, ctypes.POINTER(_i64)]),

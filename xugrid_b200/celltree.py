@@ -84,12 +84,13 @@ class OverlapStats(NamedTuple):
 
 class CellTree2d:
     def __init__(self, vertices: ArrayLike, faces: ArrayLike, fill_value: int = -1, device=None,
-                 clip_box=None, clip_targets=None):
+                 clip_box=None, clip_targets=None, clip_target_ids=None):
         """``clip_box=(xmin, xmax, ymin, ymax)`` indexes only the faces whose bounding
         box meets the box (used by ranks that own a range of target faces);
         ``clip_targets=(xy, faces, begin, end)`` (device tensors of another mesh) takes
         the box from the bounds of those target faces, reduced on the device -- no
-        host round trip."""
+        host round trip; ``clip_target_ids=(xy, faces, ids)`` the same for a list of target
+        face numbers (int32 device tensor, e.g. from ``distributed.curve_shard``)."""
         L = _native.lib()
         self.device = _device(device)
         with torch.cuda.device(self.device):
@@ -100,7 +101,17 @@ class CellTree2d:
             self.n_face, self.k = int(self.faces.shape[0]), int(self.faces.shape[1])
             self.n_node = int(self.vertices.shape[0])
             h = ctypes.c_void_p()
-            if clip_targets is not None:
+            if clip_target_ids is not None:
+                t_xy, t_faces, t_ids = clip_target_ids
+                _native.check(
+                    L.xg_index_create_for_target_ids(
+                        _native.ptr(self.vertices), self.n_node, _native.ptr(self.faces),
+                        self.faces.element_size(), self.n_face, self.k, _native.ptr(t_xy, torch.float64),
+                        _native.ptr(t_faces), t_faces.element_size(), _native.ptr(t_ids, torch.int32),
+                        int(t_ids.numel()), int(t_faces.shape[1]), _native.stream_ptr(), ctypes.byref(h),
+                    )
+                )
+            elif clip_targets is not None:
                 t_xy, t_faces, t_begin, t_end = clip_targets
                 _native.check(
                     L.xg_index_create_for_targets(
@@ -172,10 +183,12 @@ class CellTree2d:
         t_begin: int = 0,
         t_end: Optional[int] = None,
         relative: bool = False,
+        ids: Optional[torch.Tensor] = None,
     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """
         CSR over the target rows [t_begin, t_end): (indptr int64, indices int32,
-        area float64) device tensors, rows in ascending source index.
+        area float64) device tensors, rows in ascending source index.  With ``ids``
+        (int32 device tensor of target face numbers) row i belongs to face ``ids[i]``.
         """
         L = _native.lib()
         with torch.cuda.device(self.device):
@@ -184,18 +197,27 @@ class CellTree2d:
             n_t, k_t = int(fc.shape[0]), int(fc.shape[1])
             if t_end is None:
                 t_end = n_t
-            rows = t_end - t_begin
+            rows = t_end - t_begin if ids is None else int(ids.numel())
             indptr = torch.empty(rows + 1, dtype=torch.int64, device=self.device)
             nnz = ctypes.c_int64()
             job = ctypes.c_void_p()
             s = _native.stream_ptr()
-            _native.check(
-                L.xg_overlap_begin(
-                    self._h, _native.ptr(xy), int(xy.shape[0]), _native.ptr(fc), fc.element_size(),
-                    n_t, k_t, t_begin, t_end, _native.ptr(indptr), ctypes.byref(nnz), s,
-                    ctypes.byref(job),
+            if ids is None:
+                _native.check(
+                    L.xg_overlap_begin(
+                        self._h, _native.ptr(xy), int(xy.shape[0]), _native.ptr(fc), fc.element_size(),
+                        n_t, k_t, t_begin, t_end, _native.ptr(indptr), ctypes.byref(nnz), s,
+                        ctypes.byref(job),
+                    )
                 )
-            )
+            else:
+                _native.check(
+                    L.xg_overlap_begin_ids(
+                        self._h, _native.ptr(xy), int(xy.shape[0]), _native.ptr(fc), fc.element_size(),
+                        n_t, k_t, _native.ptr(ids, torch.int32), rows, _native.ptr(indptr),
+                        ctypes.byref(nnz), s, ctypes.byref(job),
+                    )
+                )
             try:
                 st = (ctypes.c_int64 * 8)()
                 _native.check(L.xg_overlap_stats(job, st))

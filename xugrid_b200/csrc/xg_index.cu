@@ -208,13 +208,15 @@ __global__ void __launch_bounds__(256)
 k_face_keys(const double2 *__restrict__ xy, const I *__restrict__ faces, int64_t f_begin,
             int64_t n, int k, const double *__restrict__ frame, uint32_t *__restrict__ keys,
             int32_t *__restrict__ ids, unsigned long long *diag2_max, const double *__restrict__ clip,
-            unsigned long long *__restrict__ kept) {
+            unsigned long long *__restrict__ kept, const int32_t *__restrict__ face_ids) {
+    // face_ids (optional): the faces to key are face_ids[f_begin + i]; what is recorded in
+    // `ids` is then the position in that list, not the face number
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     double d2 = 0.0;
     bool in_box = false;
     uint32_t my_key = 0;
     if (i < n) {
-        const I *face = faces + (f_begin + i) * k;
+        const I *face = faces + (face_ids ? (int64_t)face_ids[f_begin + i] : f_begin + i) * k;
         double2 p = xy[face[0]];
         double xmin = p.x, xmax = p.x, ymin = p.y, ymax = p.y;
 #pragma unroll
@@ -281,11 +283,11 @@ k_face_keys(const double2 *__restrict__ xy, const I *__restrict__ faces, int64_t
 template <typename I>
 __global__ void __launch_bounds__(256)
 k_face_range_bounds(const double2 *__restrict__ xy, const I *__restrict__ faces, int64_t f_begin,
-                    int64_t n, int k, unsigned long long *red) {
+                    int64_t n, int k, unsigned long long *red, const int32_t *__restrict__ face_ids) {
     double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const I *face = faces + (f_begin + i) * k;
+        const I *face = faces + (face_ids ? (int64_t)face_ids[f_begin + i] : f_begin + i) * k;
         for (int j = 0; j < k; ++j) {
             const I idx = face[j];
             if (idx < 0) break;
@@ -314,10 +316,10 @@ template <typename I, int KMAX>
 __global__ void __launch_bounds__(256)
 k_pack(const double2 *__restrict__ xy, const I *__restrict__ faces, int k,
        const int32_t *__restrict__ perm, int64_t n, Box *__restrict__ box,
-       double2 *__restrict__ poly, uint8_t *__restrict__ nvert) {
+       double2 *__restrict__ poly, uint8_t *__restrict__ nvert, const int32_t *__restrict__ face_ids) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const I *face = faces + (int64_t)perm[i] * k;
+    const I *face = faces + (int64_t)(face_ids ? face_ids[perm[i]] : perm[i]) * k;
     double2 v[KMAX];
     int len = k;
 #pragma unroll
@@ -410,28 +412,28 @@ template <typename I>
 static int launch_face_keys(const double2 *xy, const I *faces, int64_t f_begin, int64_t n, int k,
                             const double *frame, uint32_t *keys, int32_t *ids,
                             unsigned long long *diag2, const double *clip, unsigned long long *kept,
-                            cudaStream_t s) {
+                            const int32_t *face_ids, cudaStream_t s) {
     if (n == 0) return XG_OK;
     const int B = 256;
     const unsigned G = (unsigned)div_up(n, B);
-    if (k <= 3) k_face_keys<I, 3><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept);
-    else if (k <= 4) k_face_keys<I, 4><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept);
-    else k_face_keys<I, XG_MAX_N_VERTEX><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept);
+    if (k <= 3) k_face_keys<I, 3><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept, face_ids);
+    else if (k <= 4) k_face_keys<I, 4><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept, face_ids);
+    else k_face_keys<I, XG_MAX_N_VERTEX><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept, face_ids);
     XG_CHECK_LAUNCH();
     return XG_OK;
 }
 
 template <typename I>
 static int launch_pack(const double2 *xy, const I *faces, int k, const int32_t *perm, int64_t n,
-                       Box *box, double2 *poly, uint8_t *nvert, cudaStream_t s) {
+                       Box *box, double2 *poly, uint8_t *nvert, const int32_t *face_ids, cudaStream_t s) {
     if (n == 0) return XG_OK;
     const int B = 256;
     const unsigned G = (unsigned)div_up(n, B);
-    if (k <= 3) k_pack<I, 3><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert);
-    else if (k <= 4) k_pack<I, 4><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert);
-    else if (k <= 8) k_pack<I, 8><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert);
-    else if (k <= 16) k_pack<I, 16><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert);
-    else k_pack<I, XG_MAX_N_VERTEX><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert);
+    if (k <= 3) k_pack<I, 3><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert, face_ids);
+    else if (k <= 4) k_pack<I, 4><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert, face_ids);
+    else if (k <= 8) k_pack<I, 8><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert, face_ids);
+    else if (k <= 16) k_pack<I, 16><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert, face_ids);
+    else k_pack<I, XG_MAX_N_VERTEX><<<G, B, 0, s>>>(xy, faces, k, perm, n, box, poly, nvert, face_ids);
     XG_CHECK_LAUNCH();
     return XG_OK;
 }
@@ -455,7 +457,8 @@ static void ensure_pool_config() {
 
 int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
               int64_t f_end, int k, const double *d_frame, unsigned long long *d_diag2,
-              PackedMesh *out, cudaStream_t s, const double *d_clip_box, unsigned long long *d_kept) {
+              PackedMesh *out, cudaStream_t s, const double *d_clip_box, unsigned long long *d_kept,
+              const int32_t *d_face_ids) {
     ensure_pool_config();
     const int64_t n = f_end - f_begin;
     out->n = n;
@@ -470,10 +473,12 @@ int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_
     int rc;
     if (idx_bytes == 4)
         rc = launch_face_keys<int32_t>(xy, (const int32_t *)d_faces, f_begin, n, k, d_frame,
-                                       keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, clip, d_kept, s);
+                                       keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, clip, d_kept,
+                                       d_face_ids, s);
     else
         rc = launch_face_keys<int64_t>(xy, (const int64_t *)d_faces, f_begin, n, k, d_frame,
-                                       keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, clip, d_kept, s);
+                                       keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, clip, d_kept,
+                                       d_face_ids, s);
     if (rc) return rc;
     int64_t n_pack = n;
     if (clip) {
@@ -507,10 +512,10 @@ int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_
     }
     if (idx_bytes == 4)
         rc = launch_pack<int32_t>(xy, (const int32_t *)d_faces, k, out->perm, n_pack, out->box,
-                                  reinterpret_cast<double2 *>(out->poly), out->nvert, s);
+                                  reinterpret_cast<double2 *>(out->poly), out->nvert, d_face_ids, s);
     else
         rc = launch_pack<int64_t>(xy, (const int64_t *)d_faces, k, out->perm, n_pack, out->box,
-                                  reinterpret_cast<double2 *>(out->poly), out->nvert, s);
+                                  reinterpret_cast<double2 *>(out->poly), out->nvert, d_face_ids, s);
     return rc;
 }
 
@@ -530,6 +535,7 @@ struct TargetRange {
     int idx_bytes;
     int64_t begin, end;
     int k;
+    const int32_t *d_ids;  // optional: the range indexes this list of faces
 };
 
 static int launch_range_bounds(const TargetRange &t, unsigned long long *d_red, cudaStream_t s) {
@@ -537,10 +543,10 @@ static int launch_range_bounds(const TargetRange &t, unsigned long long *d_red, 
     if (n <= 0) return XG_OK;
     if (t.idx_bytes == 4)
         k_face_range_bounds<int32_t><<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)t.d_xy, (const int32_t *)t.d_faces,
-                                                               t.begin, n, t.k, d_red);
+                                                               t.begin, n, t.k, d_red, t.d_ids);
     else
         k_face_range_bounds<int64_t><<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)t.d_xy, (const int64_t *)t.d_faces,
-                                                               t.begin, n, t.k, d_red);
+                                                               t.begin, n, t.k, d_red, t.d_ids);
     XG_CHECK_LAUNCH();
     return XG_OK;
 }
@@ -634,7 +640,7 @@ static int index_create_impl(const double *d_xy, int64_t n_node, const void *d_f
         PackedMesh pm;
         pm.perm = ix->perm; pm.box = ix->leaf_box; pm.poly = ix->poly; pm.nvert = ix->nvert;
         rc = pack_mesh(d_xy, d_faces, idx_bytes, 0, n_face, k, d_frame, d_red + 4, &pm, s,
-                       culled ? d_clip : nullptr, d_red + 5);
+                       culled ? d_clip : nullptr, d_red + 5, nullptr);
         if (rc) break;
         if (culled) {
             // only the faces that can meet the box are indexed
@@ -704,8 +710,151 @@ extern "C" int xg_index_create_for_targets(const double *d_xy, int64_t n_node, c
     }
     TargetRange tr;
     tr.d_xy = d_t_xy; tr.d_faces = d_t_faces; tr.idx_bytes = t_idx_bytes;
-    tr.begin = t_begin; tr.end = t_end; tr.k = k_t;
+    tr.begin = t_begin; tr.end = t_end; tr.k = k_t; tr.d_ids = nullptr;
     return index_create_impl(d_xy, n_node, d_faces, idx_bytes, n_face, k, nullptr, &tr, stream, out);
+}
+
+extern "C" int xg_index_create_for_target_ids(const double *d_xy, int64_t n_node, const void *d_faces,
+                                              int idx_bytes, int64_t n_face, int k, const double *d_t_xy,
+                                              const void *d_t_faces, int t_idx_bytes, const int32_t *d_t_ids,
+                                              int64_t n_ids, int k_t, void *stream, xg_index **out) {
+    if (!d_t_xy || !d_t_faces || n_ids < 0 || (n_ids > 0 && !d_t_ids) || k_t < 3 ||
+        (t_idx_bytes != 4 && t_idx_bytes != 8)) {
+        set_error("xg_index_create_for_target_ids: invalid target list");
+        return XG_ERR_INVALID;
+    }
+    TargetRange tr;
+    tr.d_xy = d_t_xy; tr.d_faces = d_t_faces; tr.idx_bytes = t_idx_bytes;
+    tr.begin = 0; tr.end = n_ids; tr.k = k_t; tr.d_ids = d_t_ids;
+    return index_create_impl(d_xy, n_node, d_faces, idx_bytes, n_face, k, nullptr, &tr, stream, out);
+}
+
+// ---- partition of a mesh's faces along the space-filling curve ---------------------------
+// A rank that owns a contiguous RANGE of the caller's face numbers owns a compact patch
+// only if those numbers mean something in space.  Ownership by curve position does not
+// depend on the numbering: every rank keys all faces (same frame = bounds of the nodes,
+// so all ranks agree), counts them in 65 536 bins of the leading 16 key bits, cuts the
+// cumulative count at multiples of n / world and takes the faces of its own bins.
+namespace xg {
+
+constexpr int SHARD_BINS = 1 << 16;
+
+__global__ void __launch_bounds__(256)
+k_key_histogram(const uint32_t *__restrict__ keys, int64_t n, unsigned int *__restrict__ hist) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(hist + (keys[i] >> 16), 1u);
+}
+
+// one block: bin range [lo, hi) of `rank`; cut[r] = first bin whose cumulative count reaches
+// round(r * n / world)
+__global__ void __launch_bounds__(1024)
+k_shard_bins(const unsigned int *__restrict__ hist, int64_t n, int rank, int world, int *__restrict__ lohi) {
+    __shared__ unsigned long long s_sum[1024];
+    __shared__ int s_lo, s_hi;
+    const int per = SHARD_BINS / 1024;  // consecutive bins per thread
+    unsigned long long local = 0;
+    for (int j = 0; j < per; ++j) local += hist[threadIdx.x * per + j];
+    s_sum[threadIdx.x] = local;
+    if (threadIdx.x == 0) { s_lo = SHARD_BINS; s_hi = SHARD_BINS; }
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // inclusive scan (Hillis-Steele)
+        const unsigned long long v = threadIdx.x >= o ? s_sum[threadIdx.x - o] : 0ull;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const unsigned long long want_lo = (unsigned long long)((__int128)n * rank / world);
+    const unsigned long long want_hi = (unsigned long long)((__int128)n * (rank + 1) / world);
+    unsigned long long cum = s_sum[threadIdx.x] - local;  // faces in bins before this thread's
+    for (int j = 0; j < per; ++j) {
+        const int bin = threadIdx.x * per + j;
+        const unsigned long long next = cum + hist[bin];
+        // the bin where the cumulative count crosses the cut starts the next shard
+        if (cum < want_lo && next >= want_lo) atomicMin(&s_lo, bin + 1);
+        if (cum < want_hi && next >= want_hi) atomicMin(&s_hi, bin + 1);
+        cum = next;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        lohi[0] = rank == 0 ? 0 : s_lo;
+        lohi[1] = rank == world - 1 ? SHARD_BINS : s_hi;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_select_bins(const uint32_t *__restrict__ keys, int64_t n, const int *__restrict__ lohi,
+              int32_t *__restrict__ ids, unsigned long long *__restrict__ count) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int lo = lohi[0], hi = lohi[1];
+    bool mine = false;
+    if (i < n) {
+        const int bin = (int)(keys[i] >> 16);
+        mine = bin >= lo && bin < hi;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(count, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (mine) ids[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+    }
+}
+
+}  // namespace xg
+
+extern "C" int xg_target_shard(const double *d_xy, int64_t n_node, const void *d_faces, int idx_bytes,
+                               int64_t n_face, int k, int rank, int world, int32_t *d_ids,
+                               int64_t *h_count, void *stream) {
+    if (!h_count || n_face < 0 || n_node < 0 || k < 3 || (idx_bytes != 4 && idx_bytes != 8) || world < 1 ||
+        rank < 0 || rank >= world || (n_face > 0 && (!d_xy || !d_faces || !d_ids))) {
+        set_error("xg_target_shard: invalid argument");
+        return XG_ERR_INVALID;
+    }
+    *h_count = 0;
+    if (n_face == 0) return XG_OK;
+    if (n_face >= (int64_t)1 << 31) { set_error("xg_target_shard: more than 2^31 faces"); return XG_ERR_UNSUPPORTED; }
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf keys, ids_unused, hist, small;
+    XG_CUDA(keys.alloc(sizeof(uint32_t) * (size_t)n_face, s));
+    XG_CUDA(ids_unused.alloc(sizeof(int32_t) * (size_t)n_face, s));
+    XG_CUDA(hist.alloc(sizeof(unsigned int) * SHARD_BINS, s));
+    // small: red (8 u64) | frame (8 doubles) | lohi (2 ints) | count (u64)
+    XG_CUDA(small.alloc(256, s));
+    unsigned long long *d_red = small.as<unsigned long long>();
+    double *d_frame = reinterpret_cast<double *>(d_red + 8);
+    int *d_lohi = reinterpret_cast<int *>(d_frame + 8);
+    unsigned long long *d_count = reinterpret_cast<unsigned long long *>(d_lohi + 2);
+    XG_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned int) * SHARD_BINS, s));
+    XG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), s));
+    k_init_red<<<1, 1, 0, s>>>(d_red);
+    if (n_node > 0) k_node_bounds<<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)d_xy, n_node, d_red);
+    k_frame_from_red<<<1, 1, 0, s>>>(d_red, d_frame);
+    XG_CHECK_LAUNCH();
+    int rc;
+    if (idx_bytes == 4)
+        rc = launch_face_keys<int32_t>((const double2 *)d_xy, (const int32_t *)d_faces, 0, n_face, k, d_frame,
+                                       keys.as<uint32_t>(), ids_unused.as<int32_t>(), nullptr, nullptr, nullptr,
+                                       nullptr, s);
+    else
+        rc = launch_face_keys<int64_t>((const double2 *)d_xy, (const int64_t *)d_faces, 0, n_face, k, d_frame,
+                                       keys.as<uint32_t>(), ids_unused.as<int32_t>(), nullptr, nullptr, nullptr,
+                                       nullptr, s);
+    if (rc) return rc;
+    k_key_histogram<<<(unsigned)div_up(n_face, 256), 256, 0, s>>>(keys.as<uint32_t>(), n_face, hist.as<unsigned int>());
+    k_shard_bins<<<1, 1024, 0, s>>>(hist.as<unsigned int>(), n_face, rank, world, d_lohi);
+    k_select_bins<<<(unsigned)div_up(n_face, 256), 256, 0, s>>>(keys.as<uint32_t>(), n_face, d_lohi, d_ids, d_count);
+    XG_CHECK_LAUNCH();
+    double *slot = pinned_slot_acquire();
+    if (!slot) { set_error("xg_target_shard: no pinned host memory"); return XG_ERR_NOMEM; }
+    cudaError_t e = cudaMemcpyAsync(slot, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    unsigned long long h = 0;
+    memcpy(&h, slot, sizeof(h));
+    pinned_slot_release(slot);
+    if (e != cudaSuccess) return cuda_fail(e, "xg_target_shard", __FILE__, __LINE__);
+    *h_count = (int64_t)h;
+    return XG_OK;
 }
 
 extern "C" int xg_face_range_bounds(const double *d_xy, const void *d_faces, int idx_bytes,
@@ -724,10 +873,10 @@ extern "C" int xg_face_range_bounds(const double *d_xy, const void *d_faces, int
     if (n > 0) {
         if (idx_bytes == 4)
             k_face_range_bounds<int32_t><<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)d_xy, (const int32_t *)d_faces,
-                                                                   f_begin, n, k, red.as<unsigned long long>());
+                                                                   f_begin, n, k, red.as<unsigned long long>(), nullptr);
         else
             k_face_range_bounds<int64_t><<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)d_xy, (const int64_t *)d_faces,
-                                                                   f_begin, n, k, red.as<unsigned long long>());
+                                                                   f_begin, n, k, red.as<unsigned long long>(), nullptr);
     }
     k_frame_from_red<<<1, 1, 0, s>>>(red.as<unsigned long long>(), frame.as<double>());
     XG_CHECK_LAUNCH();

@@ -39,23 +39,25 @@ namespace xg {
 
 constexpr int TRAV_WARPS = 8;
 constexpr int TRAV_STACK = 256;
-#ifndef XG_TRAV_PREFETCH
-#define XG_TRAV_PREFETCH 1
+#ifndef XG_TRAV_WIN
+#define XG_TRAV_WIN 256
 #endif
-#ifndef XG_TRAV_QCAP
-#define XG_TRAV_QCAP 192
-#endif
-constexpr int TRAV_QCAP = XG_TRAV_QCAP;         // pair queue entries per warp; flushed when the next node's pairs do not fit
+constexpr int TRAV_WIN = XG_TRAV_WIN;           // pairs per window of the arena (reserved ahead by a warp)
+constexpr int TRAV_BLOCKS_PER_SM = 4;           // resident blocks of the persistent walk
 constexpr int PAIRS_PER_TARGET_GUESS = 16;
 
 // device counters of one job
-enum { CTR_VISITS = 0, CTR_TESTS = 1, CTR_PAIRS = 2, CTR_SURV = 3, CTR_HUGE = 5, CTR_LONG = 6, CTR_N = 8 };
+// CTR_PAIRS / CTR_SURV count arena SLOTS (reserved windows, unused tails included);
+// CTR_CAND / CTR_NSURV the candidate pairs / survivors themselves
+enum { CTR_VISITS = 0, CTR_TESTS = 1, CTR_PAIRS = 2, CTR_SURV = 3, CTR_CAND = 4, CTR_HUGE = 5, CTR_LONG = 6, CTR_NSURV = 7, CTR_N = 8 };
 
 struct TraverseParams {
     const Box *boxes[MAX_LEVELS + 1];  // [0] = leaves, [d] = node level d-1
     int64_t count[MAX_LEVELS + 1];
     int top;                           // depth of the virtual root
 };
+
+__device__ __forceinline__ int64_t div_up_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ bool boxes_intersect(const Box &a, const Box &b) {
     // strict: touching boxes do not intersect.  Bitwise &: all four compares are
@@ -77,6 +79,9 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
                  : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+// waits until at most one committed group of this thread is still in flight
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 // loads whose position in the instruction stream matters (software pipelining):
 // a volatile asm is not moved across the other volatile asms around it
 __device__ __forceinline__ int2 ld_int2_here(const int2 *p) {
@@ -90,170 +95,164 @@ __device__ __forceinline__ int64_t ld_i64_here(const int64_t *p) {
     return (int64_t)v;
 }
 __device__ __forceinline__ void schedule_fence() { asm volatile("" ::: "memory"); }
-__device__ __forceinline__ Box ld_box_here(const Box *p) {
-    Box b;
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];\n" : "=d"(b.xmin), "=d"(b.xmax) : "l"(p));
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2+16];\n" : "=d"(b.ymin), "=d"(b.ymax) : "l"(p));
-    return b;
+__device__ __forceinline__ int32_t atomic_add_here(int32_t *p, int32_t v) {
+    int32_t old;
+    asm volatile("atom.global.add.s32 %0, [%1], %2;\n" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
 }
 
-// pairs[i] = {sorted target position, sorted source position}
+// pairs[i] = {sorted target position, sorted source position}, or {-1, -1} for an unused
+// slot of a window.
+//
+// Persistent: a block takes groups of TRAV_WARPS consecutive tiles in grid-stride order, a
+// warp one tile of each group.  Candidate pairs are written to the arena in WINDOWS of
+// TRAV_WIN slots that a warp reserves ahead of time: the reservation (one atomicAdd on the
+// arena counter) is issued right after the previous window was written and its result is
+// first needed a window of work later.  The first version reserved exactly the pairs it
+// had (one atomicAdd per flush and per tile, result needed at once): ncu showed 40 % of
+// the kernel's stall samples on the shuffle that broadcasts that result -- several 100 k
+// round trips to one hot address.  Cost of the windows: the unused tail of every warp's
+// last window (< 1 % of the arena at 10 M targets), marked invalid.
 __global__ void __launch_bounds__(TRAV_WARPS * 32)
 k_traverse(const TraverseParams P, const Box *__restrict__ tbox, int64_t n_t, int tile_stride,
            int2 *__restrict__ pairs, unsigned long long cap, int32_t *__restrict__ cand_cnt,
            unsigned long long *__restrict__ ctr) {
     __shared__ Box s_node[TRAV_WARPS][32];
     __shared__ int32_t s_stack[TRAV_WARPS][TRAV_STACK];
-    __shared__ int2 s_q[TRAV_WARPS][TRAV_QCAP];
+    __shared__ int2 s_q[TRAV_WARPS][TRAV_WIN];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile_stride > 1: density sampling pass (every tile_stride-th tile, cap == 0: count only)
-    const int64_t tile = (blockIdx.x * (int64_t)TRAV_WARPS + w) * tile_stride;
-    const int64_t t = tile * 32 + lane;
-    if (tile * 32 >= n_t) return;
-    const bool valid = t < n_t;
-    Box tb;
-    if (valid) tb = tbox[t];
-    else { tb.xmin = INFINITY; tb.xmax = -INFINITY; tb.ymin = INFINITY; tb.ymax = -INFINITY; }
-    Box ub = tb;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ub.xmin = fmin(ub.xmin, __shfl_xor_sync(0xffffffffu, ub.xmin, o));
-        ub.xmax = fmax(ub.xmax, __shfl_xor_sync(0xffffffffu, ub.xmax, o));
-        ub.ymin = fmin(ub.ymin, __shfl_xor_sync(0xffffffffu, ub.ymin, o));
-        ub.ymax = fmax(ub.ymax, __shfl_xor_sync(0xffffffffu, ub.ymax, o));
-    }
-    int sp = 1, qn = 0;
-    if (lane == 0) s_stack[w][0] = P.top << 27;
-    unsigned visits = 0, tests = 0;
-    int my_cand = 0;  // candidates of this lane's target = capacity of its provisional row
+    const int64_t n_tiles = div_up_dev(div_up_dev(n_t, 32), tile_stride);
+    const int64_t n_groups = div_up_dev(n_tiles, TRAV_WARPS);
+    if ((int64_t)blockIdx.x * TRAV_WARPS + w >= n_tiles) return;  // this warp never gets a tile
 
-    auto flush = [&]() {
+    unsigned long long win = 0;  // start of the reserved window (lane 0)
+    if (lane == 0) win = atomicAdd(ctr + CTR_PAIRS, (unsigned long long)TRAV_WIN);
+    int qn = 0;
+    unsigned visits = 0, tests = 0;
+    unsigned long long real_pairs = 0;
+
+    // writes the full window and reserves the next one
+    auto flush_window = [&]() {
         __syncwarp();
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(ctr + CTR_PAIRS, (unsigned long long)qn);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (int i = lane; i < qn; i += 32)
+        const unsigned long long base = __shfl_sync(0xffffffffu, win, 0);
+        for (int i = lane; i < TRAV_WIN; i += 32)
             if (base + i < cap) pairs[base + i] = s_q[w][i];
         __syncwarp();
-        qn = 0;
+        if (lane == 0) win = atomicAdd(ctr + CTR_PAIRS, (unsigned long long)TRAV_WIN);
     };
 
-    // The walk is a chain of dependent node loads (pop -> load 32 child boxes -> test -> push),
-    // and since the per-lane hit masks took the instruction count down it is bound by that
-    // latency, not by issue slots: the boxes of the NEXT stack entry are requested before the
-    // current node is processed.  (The order of the walk changes -- the entry below the top
-    // is visited before the children the current node pushes -- which no result depends on.)
     auto load_node = [&](int32_t entry) {
         const int d = entry >> 27;
         const int64_t c0 = (int64_t)(entry & 0x7ffffff) * FANOUT;
         const int64_t nc = P.count[d - 1] - c0;
         Box b;
         b.xmin = INFINITY; b.xmax = -INFINITY; b.ymin = INFINITY; b.ymax = -INFINITY;
-        if (lane < nc) b = ld_box_here(P.boxes[d - 1] + c0 + lane);
+        if (lane < nc) b = P.boxes[d - 1][c0 + lane];
         return b;
     };
-    __syncwarp();
-    int32_t entry = s_stack[w][--sp];
-    Box mine = load_node(entry);
-    while (true) {
-#if XG_TRAV_PREFETCH
-        int32_t entry_next = -1;
-        Box mine_next;
-        if (sp > 0) {
-            entry_next = s_stack[w][--sp];
-            mine_next = load_node(entry_next);
-        }
-        schedule_fence();
-#endif
-        const int d = entry >> 27;
-        const int64_t c0 = (int64_t)(entry & 0x7ffffff) * FANOUT;
-        ++visits;
-        unsigned m = __ballot_sync(0xffffffffu, boxes_intersect(mine, ub));
-        __syncwarp();
-        if (m != 0) {
-        s_node[w][lane] = mine;
-        __syncwarp();
-        if (d > 1) {
-            while (m) {
-                const int c = __ffs(m) - 1;
-                m &= m - 1;
-                const Box b = s_node[w][c];
-                if (__any_sync(0xffffffffu, boxes_intersect(tb, b))) {
-                    if (lane == 0) s_stack[w][sp] = ((d - 1) << 27) | (int32_t)(c0 + c);
-                    ++sp;
-                }
-            }
-        } else {
-            tests += __popc(m);
-            // every lane collects the children that meet ITS target as a bit mask (two
-            // children per trip: both boxes are loaded before either is tested); nothing
-            // is voted or queued per child
-            unsigned hits = 0u;
-            while (m) {
-                const int ca = __ffs(m) - 1;
-                m &= m - 1;
-                const bool two = m != 0u;
-                const int cb2 = two ? __ffs(m) - 1 : ca;
-                m &= m - 1;
-                const Box ba = s_node[w][ca], bb = s_node[w][cb2];
-                const bool ha = boxes_intersect(tb, ba), hb = two & boxes_intersect(tb, bb);
-                hits |= (ha ? 1u : 0u) << ca;
-                hits |= (hb ? 1u : 0u) << cb2;
-            }
-            const int n_mine = __popc(hits);
-            my_cand += n_mine;
-            int incl = n_mine;  // inclusive prefix sum over the lanes
+
+    for (int64_t group = blockIdx.x; group < n_groups; group += gridDim.x) {
+        const int64_t tile = (group * TRAV_WARPS + w) * tile_stride;
+        const int64_t t = tile * 32 + lane;
+        if (tile * 32 >= n_t) break;
+        const bool valid = t < n_t;
+        Box tb;
+        if (valid) tb = tbox[t];
+        else { tb.xmin = INFINITY; tb.xmax = -INFINITY; tb.ymin = INFINITY; tb.ymax = -INFINITY; }
+        Box ub = tb;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                incl += lane >= o ? v : 0;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total > 0) {
-                if (qn > 0 && qn + total > TRAV_QCAP) flush();
-                if (total <= TRAV_QCAP) {
-                    // a lane appends its own pairs: the queue (and so the arena) holds the
-                    // pairs of a node grouped by target
-                    int pos = qn + incl - n_mine;
-                    while (hits) {
-                        const int c = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        s_q[w][pos++] = make_int2((int32_t)t, (int32_t)(c0 + c));
+        for (int o = 16; o > 0; o >>= 1) {
+            ub.xmin = fmin(ub.xmin, __shfl_xor_sync(0xffffffffu, ub.xmin, o));
+            ub.xmax = fmax(ub.xmax, __shfl_xor_sync(0xffffffffu, ub.xmax, o));
+            ub.ymin = fmin(ub.ymin, __shfl_xor_sync(0xffffffffu, ub.ymin, o));
+            ub.ymax = fmax(ub.ymax, __shfl_xor_sync(0xffffffffu, ub.ymax, o));
+        }
+        int sp = 1;
+        if (lane == 0) s_stack[w][0] = P.top << 27;
+        int my_cand = 0;  // candidates of this lane's target = capacity of its provisional row
+        __syncwarp();
+        while (sp > 0) {
+            const int32_t entry = s_stack[w][--sp];
+            const int d = entry >> 27;
+            const int64_t c0 = (int64_t)(entry & 0x7ffffff) * FANOUT;
+            const Box mine = load_node(entry);
+            ++visits;
+            unsigned m = __ballot_sync(0xffffffffu, boxes_intersect(mine, ub));
+            __syncwarp();
+            if (m == 0) continue;
+            s_node[w][lane] = mine;
+            __syncwarp();
+            if (d > 1) {
+                while (m) {
+                    const int c = __ffs(m) - 1;
+                    m &= m - 1;
+                    const Box b = s_node[w][c];
+                    if (__any_sync(0xffffffffu, boxes_intersect(tb, b))) {
+                        if (lane == 0) s_stack[w][sp] = ((d - 1) << 27) | (int32_t)(c0 + c);
+                        ++sp;
                     }
+                }
+            } else {
+                tests += __popc(m);
+                // every lane collects the children that meet ITS target as a bit mask (two
+                // children per trip: both boxes are loaded before either is tested); nothing
+                // is voted or queued per child
+                unsigned hits = 0u;
+                while (m) {
+                    const int ca = __ffs(m) - 1;
+                    m &= m - 1;
+                    const bool two = m != 0u;
+                    const int cb2 = two ? __ffs(m) - 1 : ca;
+                    m &= m - 1;
+                    const Box ba = s_node[w][ca], bb = s_node[w][cb2];
+                    const bool ha = boxes_intersect(tb, ba), hb = two & boxes_intersect(tb, bb);
+                    hits |= (ha ? 1u : 0u) << ca;
+                    hits |= (hb ? 1u : 0u) << cb2;
+                }
+                const int n_mine = __popc(hits);
+                my_cand += n_mine;
+                int incl = n_mine;  // inclusive prefix sum over the lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    incl += lane >= o ? v : 0;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total > 0) {
+                    // a lane appends its own pairs (the pairs of a node are grouped by target);
+                    // whenever the window is full it goes out and the rest continues in the next
+                    int pos = qn + incl - n_mine;
                     qn += total;
-                } else {
-                    // more pairs from one node than the queue holds (targets much larger
-                    // than the source faces): straight to the arena
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(ctr + CTR_PAIRS, (unsigned long long)total);
-                    base = __shfl_sync(0xffffffffu, base, 0) + (unsigned long long)(incl - n_mine);
-                    while (hits) {
-                        const int c = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        if (base < cap) pairs[base] = make_int2((int32_t)t, (int32_t)(c0 + c));
-                        ++base;
+                    real_pairs += (unsigned long long)total;
+                    while (true) {
+                        while (hits != 0u && pos < TRAV_WIN) {
+                            const int c = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            s_q[w][pos++] = make_int2((int32_t)t, (int32_t)(c0 + c));
+                        }
+                        if (qn < TRAV_WIN) break;
+                        flush_window();
+                        qn -= TRAV_WIN;
+                        pos -= TRAV_WIN;
                     }
                 }
             }
+            __syncwarp();
         }
-        }
-        __syncwarp();
-#if XG_TRAV_PREFETCH
-        if (entry_next >= 0) {
-            entry = entry_next;
-            mine = mine_next;
-            continue;
-        }
-#endif
-        if (sp == 0) break;
-        entry = s_stack[w][--sp];
-        mine = load_node(entry);
+        if (valid && cand_cnt) cand_cnt[t] = my_cand;
     }
-    if (qn > 0) flush();
-    if (valid && cand_cnt) cand_cnt[t] = my_cand;
+    // the last window: what is queued, the rest marked unused
+    __syncwarp();
+    {
+        const unsigned long long base = __shfl_sync(0xffffffffu, win, 0);
+        for (int i = lane; i < TRAV_WIN; i += 32)
+            if (base + i < cap) pairs[base + i] = i < qn ? s_q[w][i] : make_int2(-1, -1);
+    }
     if (lane == 0) {
         atomicAdd(ctr + CTR_VISITS, (unsigned long long)visits);
         atomicAdd(ctr + CTR_TESTS, (unsigned long long)tests * 32ull);
+        atomicAdd(ctr + CTR_CAND, real_pairs);
     }
 }
 
@@ -290,16 +289,20 @@ __device__ __noinline__ double clip_area_fallback(const double2 *pa, int na, con
     return clip_area<KT, KS>(a, na, b, nb, bufA, bufB, stride);
 }
 
-constexpr int SAT_QCAP = 96;    // survivor queue entries per warp
-constexpr int SAT_QFLUSH = 64;  // flush threshold (one trip adds <= 32)
-constexpr int SAT_RUN = 8;      // consecutive 32-pair groups per warp
+constexpr int SAT_WIN = 64;                 // survivors per window of the survivor list (reserved ahead, as in the walk)
+constexpr int SAT_QCAP = SAT_WIN + 32;      // survivor queue entries per warp (one trip adds <= 32)
+constexpr int SAT_RUN = 8;                  // consecutive 32-pair groups per warp (>= 4)
 
 // One thread per candidate pair, warp-uniform grid-stride trips.  Like the clip
 // kernel it is software-pipelined: the polygons of the thread's next pair are
 // staged into shared memory with cp.async while the current pair is tested, the
 // pair record after that is in flight to a register.  Survivors are compacted
-// with a warp vote into a per-warp queue and appended to the dense survivor list
-// with one global atomic per >= 64 entries (no block-wide barrier).
+// with a warp vote into a per-warp queue and written to the survivor list in windows
+// of SAT_WIN slots reserved one window ahead (no block-wide barrier, no wait for the
+// atomic; the tail of a warp's last window is marked unused with {-1, -1}).
+#ifndef XG_SAT_FP32
+#define XG_SAT_FP32 1
+#endif
 #ifndef XG_SAT_MINB
 #define XG_SAT_MINB 3
 #endif
@@ -320,24 +323,32 @@ k_sat(const int2 *__restrict__ pairs, unsigned long long cap, const double2 *__r
     // with the exact capacity the walk counted
     if (n_pairs > cap) return;
 
-    auto stage = [&](const int2 r) {
+    constexpr int M = KT + KS;
+    auto stage = [&](const int2 r, int sl) {
         const double2 *tp = tpoly + (int64_t)r.x * kt;
         const double2 *sp = spoly + (int64_t)r.y * ks;
+        double2 *dst = stg + (size_t)sl * M * BT;
 #pragma unroll
         for (int j = 0; j < KT; ++j)
-            if (j < kt) cp_async16(stg + j * BT, tp + j);
+            if (j < kt) cp_async16(dst + j * BT, tp + j);
 #pragma unroll
         for (int j = 0; j < KS; ++j)
-            if (j < ks) cp_async16(stg + (KT + j) * BT, sp + j);
+            if (j < ks) cp_async16(dst + (KT + j) * BT, sp + j);
     };
-    auto flush = [&](int &qn) {
+    unsigned long long win = 0;  // start of the reserved window (lane 0)
+    // writes the first SAT_WIN queued survivors, moves the rest (< 32) to the front of the
+    // queue and reserves the next window
+    auto flush_window = [&](int &qn) {
         __syncwarp();
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(ctr + CTR_SURV, (unsigned long long)qn);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (int i = lane; i < qn; i += 32) surv[base + i] = s_q[w][i];
+        const unsigned long long base = __shfl_sync(0xffffffffu, win, 0);
+        for (int i = lane; i < SAT_WIN; i += 32) surv[base + i] = s_q[w][i];
+        const int rest = qn - SAT_WIN;
+        const int2 moved = lane < rest ? s_q[w][SAT_WIN + lane] : make_int2(0, 0);
         __syncwarp();
-        qn = 0;
+        if (lane < rest) s_q[w][lane] = moved;
+        if (lane == 0) win = atomicAdd(ctr + CTR_SURV, (unsigned long long)SAT_WIN);
+        __syncwarp();
+        qn = rest;
     };
 
     // a warp takes SAT_RUN consecutive groups of 32 pairs before it jumps ahead, so that
@@ -347,39 +358,70 @@ k_sat(const int2 *__restrict__ pairs, unsigned long long cap, const double2 *__r
     const unsigned long long gw = (unsigned long long)blockIdx.x * (BT / 32) + w;
     const unsigned long long n_gw = (unsigned long long)gridDim.x * (BT / 32);
     const unsigned long long jump = (n_gw * SAT_RUN - (SAT_RUN - 1)) * 32ull;  // last group of a run -> next run
-    unsigned long long p = gw * SAT_RUN * 32ull + lane, p1 = p + 32, p2 = p + 64;
-    int t2 = 2;  // position of p2 inside its run (SAT_RUN >= 3)
-    int2 r = make_int2(0, 0), r_next = make_int2(0, 0);
-    int na = 3, nb = 3;
-    if (p < n_pairs) {
-        r = pairs[p];
-        stage(r);
-        if (KT > 3) na = tnv[r.x] & 0x7f;
-        if (KS > 3) nb = snv[r.y] & 0x7f;
+    // positions of this thread's current pair and of the three after it; tN = place of pN in its run
+    unsigned long long p0 = gw * SAT_RUN * 32ull + lane, p1 = p0 + 32, p2 = p0 + 64, p3 = p0 + 96;
+    int t3 = 3;  // (SAT_RUN >= 4)
+    if (p0 - lane >= n_pairs) return;  // this warp has no pairs
+    if (lane == 0) win = atomicAdd(ctr + CTR_SURV, (unsigned long long)SAT_WIN);
+    // Software pipeline, two trips deep (ncu on the one-trip version: 15 % of all stall samples
+    // on the wait for the staged polygons): while pair p0 is tested, the polygons of p1 are
+    // landing in the other staging slot, those of p2 are requested into the slot p0 has just
+    // been read from, and the record of p3 is in flight to a register.
+    // (an unused slot of the arena, {-1, -1}, is staged as pair {0, 0} and never passes)
+    int2 r0 = make_int2(-1, -1), r1 = make_int2(-1, -1), r2 = make_int2(-1, -1);
+    int na0 = 3, nb0 = 3, na1 = 3, nb1 = 3;
+    int slot = 0;
+    auto stage_checked = [&](const int2 rec, int sl, int &na, int &nb) {
+        const int2 safe = rec.x >= 0 ? rec : make_int2(0, 0);
+        stage(safe, sl);
+        if (KT > 3) na = tnv[safe.x] & 0x7f;
+        if (KS > 3) nb = snv[safe.y] & 0x7f;
+    };
+    if (p0 < n_pairs) {
+        r0 = pairs[p0];
+        stage_checked(r0, 0, na0, nb0);
     }
-    if (p1 < n_pairs) r_next = pairs[p1];
+    cp_async_commit();
+    if (p1 < n_pairs) {
+        r1 = pairs[p1];
+        stage_checked(r1, 1, na1, nb1);
+    }
+    cp_async_commit();
+    if (p2 < n_pairs) r2 = pairs[p2];
     int qn = 0;
+    unsigned n_pass = 0;
     // (warp-uniform trip count: the first pair of the warp's group decides)
 #pragma unroll 1
-    while (p - lane < n_pairs) {
-        const bool valid = p < n_pairs;
-        cp_async_wait_all();
+    while (p0 - lane < n_pairs) {
+        const bool valid = p0 < n_pairs && r0.x >= 0;
+        cp_async_wait_but_one();  // the older of the two groups in flight: the polygons of p0
+        const double2 *cur = stg + (size_t)slot * M * BT;
         double2 a[KT], b[KS];
 #pragma unroll
-        for (int jj = 0; jj < KT; ++jj) a[jj] = stg[jj * BT];
+        for (int jj = 0; jj < KT; ++jj) a[jj] = cur[jj * BT];
 #pragma unroll
-        for (int jj = 0; jj < KS; ++jj) b[jj] = stg[(KT + jj) * BT];
-        const int2 r_cur = r;
-        const int na_cur = na, nb_cur = nb;
-        if (p1 < n_pairs) {
-            r = r_next;
-            stage(r);
-            if (KT > 3) na = tnv[r.x] & 0x7f;
-            if (KS > 3) nb = snv[r.y] & 0x7f;
-        }
-        if (p2 < n_pairs) r_next = ld_int2_here(pairs + p2);
+        for (int jj = 0; jj < KS; ++jj) b[jj] = cur[(KT + jj) * BT];
+        const int2 r_cur = r0;
+        const int na_cur = na0, nb_cur = nb0;
+        r0 = r1; na0 = na1; nb0 = nb1;
+        r1 = r2;
+        if (p2 < n_pairs) stage_checked(r1, slot, na1, nb1);
+        cp_async_commit();  // (an empty group when nothing was staged keeps the count right)
+        if (p3 < n_pairs) r2 = ld_int2_here(pairs + p3);
         schedule_fence();
         bool pass = false;
+#if XG_SAT_FP32
+        if (KT <= 4 && KS <= 4) {
+            // fp32 pre-decision (xg_geom.cuh): certain for all but the pairs within rounding
+            // distance of a tie; a warp that holds such a pair runs the fp64 test as well
+            const int pre = valid ? polygons_intersect_fp32<KT, KS>(a, na_cur, b, nb_cur) : SAT_REJECT;
+            pass = pre == SAT_ACCEPT;
+            if (__any_sync(0xffffffffu, pre == SAT_AMBIGUOUS)) {
+                const bool exact = polygons_intersect_uniform<KT, KS>(a, na_cur, b, nb_cur);
+                if (pre == SAT_AMBIGUOUS) pass = exact;
+            }
+        } else
+#endif
         if (valid) {
             if (KT <= 8 && KS <= 8) pass = polygons_intersect_uniform<KT, KS>(a, na_cur, b, nb_cur);
             else pass = polygons_intersect<KT, KS>(a, na_cur, b, nb_cur);
@@ -387,14 +429,24 @@ k_sat(const int2 *__restrict__ pairs, unsigned long long cap, const double2 *__r
         const unsigned m = __ballot_sync(0xffffffffu, pass);
         if (pass) s_q[w][qn + __popc(m & lt_mask)] = r_cur;
         qn += __popc(m);
-        if (qn >= SAT_QFLUSH) flush(qn);
-        p = p1;
+        n_pass += __popc(m);
+        if (qn >= SAT_WIN) flush_window(qn);
+        p0 = p1;
         p1 = p2;
-        ++t2;
-        p2 += (t2 == SAT_RUN) ? jump : 32ull;
-        t2 = (t2 == SAT_RUN) ? 0 : t2;
+        p2 = p3;
+        ++t3;
+        p3 += (t3 == SAT_RUN) ? jump : 32ull;
+        t3 = (t3 == SAT_RUN) ? 0 : t3;
+        slot ^= 1;
     }
-    if (qn > 0) flush(qn);
+    cp_async_wait_all();
+    // the last window: what is queued, the rest marked unused
+    __syncwarp();
+    {
+        const unsigned long long base = __shfl_sync(0xffffffffu, win, 0);
+        for (int i = lane; i < SAT_WIN; i += 32) surv[base + i] = i < qn ? s_q[w][i] : make_int2(-1, -1);
+    }
+    if (lane == 0) atomicAdd(ctr + CTR_NSURV, (unsigned long long)n_pass);
 }
 
 // One thread per survivor, grid-stride.  The kernel is bound by the latency of
@@ -441,12 +493,17 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
     int2 r = make_int2(0, 0), r_next = make_int2(0, 0);
     int64_t base = 0;    // prov_ptr of the staged survivor's target
     int na = 3, nb = 3;  // vertex counts (looked up for K > 3 only)
+    // (an unused slot of the survivor list, {-1, -1}, is staged as pair {0, 0}; its area is dropped)
+    auto stage_checked = [&](const int2 rec) {
+        const int2 safe = rec.x >= 0 ? rec : make_int2(0, 0);
+        stage(safe);
+        base = ld_i64_here(prov_ptr + safe.x);
+        if (KT > 3) na = tnv[safe.x] & 0x7f;
+        if (KS > 3) nb = snv[safe.y] & 0x7f;
+    };
     if (q < n_surv) {
         r = surv[q];
-        stage(r);
-        base = prov_ptr[r.x];
-        if (KT > 3) na = tnv[r.x] & 0x7f;
-        if (KS > 3) nb = snv[r.y] & 0x7f;
+        stage_checked(r);
     }
     if (q + stride < n_surv) r_next = surv[q + stride];
     int2 pend_r = make_int2(-1, 0);  // x < 0: nothing pending
@@ -454,8 +511,7 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
     double pend_ar = 0.0;
     for (; q < n_surv; q += stride) {
         cp_async_wait_all();
-        int32_t slot = 0;
-        if (pend_r.x >= 0) slot = atomicAdd(fill_cnt + pend_r.x, 1);
+        uint32_t slot = 0;
         double2 a[KT], b[KS];
 #pragma unroll
         for (int j = 0; j < KT; ++j) a[j] = stg[j * BT];
@@ -467,35 +523,39 @@ k_clip_survivors(const int2 *__restrict__ surv, const unsigned long long *__rest
         // ---- prefetch
         if (q + stride < n_surv) {
             r = r_next;
-            stage(r);
-            base = ld_i64_here(prov_ptr + r.x);
-            if (KT > 3) na = tnv[r.x] & 0x7f;
-            if (KS > 3) nb = snv[r.y] & 0x7f;
+            stage_checked(r);
         }
         if (q + 2 * stride < n_surv) r_next = ld_int2_here(surv + q + 2 * stride);
         schedule_fence();
+        // the slot of the pending entry: requested here, consumed after the clip
+        if (pend_r.x >= 0) slot = (uint32_t)atomic_add_here(fill_cnt + pend_r.x, 1);
         // ---- clip
         double ar;
         if (KT + KS <= 32) {
             bool fb = false;
             ar = clip_area_masks<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT, &fb);
-            if (fb)
+            if (fb && r_cur.x >= 0)
                 ar = clip_area_fallback<KT, KS>(tpoly + (int64_t)r_cur.x * kt, na_cur,
                                                 spoly + (int64_t)r_cur.y * ks, nb_cur, bufA, bufB, BT);
         } else {
             ar = clip_area<KT, KS>(a, na_cur, b, nb_cur, bufA, bufB, BT);
         }
         schedule_fence();  // keeps the stores of the pending entry late
+        // ptxas widened the slot to 64 bits for the address right behind the atomic -- a wait for
+        // its whole round trip before the clip had even started (ncu: 20 % of the kernel's
+        // stall samples on that one shift).  Opaque until here: nothing derived from it can
+        // be computed earlier.
+        asm volatile("" : "+r"(slot));
         if (pend_r.x >= 0) {
             prov_col[pend_base + slot] = pend_r.y;
             prov_val[pend_base + slot] = pend_ar;
         }
-        pend_r = (ar > 0.0) ? r_cur : make_int2(-1, 0);
+        pend_r = (ar > 0.0 && r_cur.x >= 0) ? r_cur : make_int2(-1, 0);
         pend_base = base_cur;
         pend_ar = ar;
     }
     if (pend_r.x >= 0) {
-        const int32_t slot = atomicAdd(fill_cnt + pend_r.x, 1);
+        const uint32_t slot = (uint32_t)atomicAdd(fill_cnt + pend_r.x, 1);
         prov_col[pend_base + slot] = pend_r.y;
         prov_val[pend_base + slot] = pend_ar;
     }
@@ -762,7 +822,8 @@ struct ClipArgs {
 template <int KT, int KS, int BT, int MINB>
 static int launch_clip(const ClipArgs &A, cudaStream_t s) {
     int per_sm = 1;
-    const size_t smem_sat = sizeof(double2) * (size_t)(KT + KS) * BT;  // one staged pair per thread
+    const size_t smem_sat = sizeof(double2) * 2 * (size_t)(KT + KS) * BT;  // two staged pairs per thread
+    XG_CUDA(cudaFuncSetAttribute(k_sat<KT, KS, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sat));
     XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sat<KT, KS, BT>, BT, smem_sat));
     if (per_sm < 1) per_sm = 1;
     k_sat<KT, KS, BT><<<NUM_SMS * per_sm, BT, smem_sat, s>>>(A.pairs, A.cap, (const double2 *)A.tpoly, A.tnv, A.kt,
@@ -825,6 +886,13 @@ static TraverseParams traverse_params(const xg_index *source) {
     return P;
 }
 
+// blocks of the persistent walk over `tiles` tiles of 32 targets
+static unsigned traverse_grid(int64_t tiles) {
+    const int64_t groups = div_up(tiles, TRAV_WARPS);
+    const int64_t resident = (int64_t)NUM_SMS * TRAV_BLOCKS_PER_SM;
+    return (unsigned)(groups < resident ? (groups > 0 ? groups : 1) : resident);
+}
+
 // Candidate density of a job whose source mesh is much finer than its targets: walk
 // every SAMPLE_STRIDE-th tile without storing anything and scale the count, so that
 // the pair arena is sized right the first time (otherwise the full walk runs twice).
@@ -834,14 +902,16 @@ static int estimate_candidates(xg_overlap *job, unsigned long long *estimate) {
     const int64_t tiles = div_up(job->n_t, 32);
     const int64_t sampled = div_up(tiles, SAMPLE_STRIDE);
     XG_CUDA(cudaMemsetAsync(job->ctr.p, 0, sizeof(unsigned long long) * CTR_N, s));
-    k_traverse<<<(unsigned)div_up(sampled, TRAV_WARPS), TRAV_WARPS * 32, 0, s>>>(
+    k_traverse<<<traverse_grid(sampled), TRAV_WARPS * 32, 0, s>>>(
         traverse_params(job->src), job->tbox.as<Box>(), job->n_t, SAMPLE_STRIDE, nullptr, 0ull, nullptr,
         job->ctr.as<unsigned long long>());
     XG_CHECK_LAUNCH();
     unsigned long long h = 0;
-    XG_CUDA(cudaMemcpyAsync(&h, job->ctr.as<unsigned long long>() + CTR_PAIRS, sizeof(h), cudaMemcpyDeviceToHost, s));
+    XG_CUDA(cudaMemcpyAsync(&h, job->ctr.as<unsigned long long>() + CTR_CAND, sizeof(h), cudaMemcpyDeviceToHost, s));
     XG_CUDA(cudaStreamSynchronize(s));
-    *estimate = (unsigned long long)((double)h * (double)tiles / (double)sampled * 1.25) + 65536ull;
+    // (+ the unused tails of the last windows of the persistent walk's warps)
+    *estimate = (unsigned long long)((double)h * (double)tiles / (double)sampled * 1.25) + 65536ull +
+                (unsigned long long)traverse_grid(tiles) * TRAV_WARPS * TRAV_WIN;
     return XG_OK;
 }
 
@@ -857,7 +927,8 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
 
     XG_CUDA(cudaMemsetAsync(job->ctr.p, 0, sizeof(unsigned long long) * CTR_N, s));
     XG_CUDA(job->pairs.alloc(sizeof(int2) * (size_t)cap, s));
-    XG_CUDA(job->surv.alloc(sizeof(int2) * (size_t)cap, s));
+    // (+ the unused tails of the last survivor windows: at most 8 blocks of 8 warps per SM)
+    XG_CUDA(job->surv.alloc(sizeof(int2) * ((size_t)cap + (size_t)NUM_SMS * 64 * SAT_WIN), s));
     XG_CUDA(job->prov_col.alloc(sizeof(int32_t) * (size_t)cap, s));
     // cnt = [cand_cnt | fill_cnt | row_cnt], (n_t + 1) int32 each
     XG_CUDA(cudaMemsetAsync(job->cnt.p, 0, sizeof(int32_t) * 2 * (size_t)(n_t + 1), s));
@@ -866,7 +937,7 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
     const TraverseParams P = traverse_params(source);
     const unsigned tiles = (unsigned)div_up(n_t, 32);
     XG_CUDA(job->mark());  // XG_PHASE_TRAVERSE
-    k_traverse<<<(unsigned)div_up(tiles, TRAV_WARPS), TRAV_WARPS * 32, 0, s>>>(
+    k_traverse<<<traverse_grid(tiles), TRAV_WARPS * 32, 0, s>>>(
         P, job->tbox.as<Box>(), n_t, 1, job->pairs.as<int2>(), cap, cand_cnt,
         job->ctr.as<unsigned long long>());
     XG_CHECK_LAUNCH();
@@ -933,25 +1004,27 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
     if (hc[CTR_PAIRS] > cap) return XG_OK;  // caller re-runs
     job->collect();
     job->nnz = nnz;
-    job->n_cand = (int64_t)hc[CTR_PAIRS];
-    job->n_surv = (int64_t)hc[CTR_SURV];
+    job->n_cand = (int64_t)hc[CTR_CAND];
+    job->n_surv = (int64_t)hc[CTR_NSURV];
     job->h_stats[0] = n_t;
     job->h_stats[1] = (int64_t)hc[CTR_VISITS];
     job->h_stats[2] = (int64_t)hc[CTR_TESTS];
-    job->h_stats[3] = (int64_t)hc[CTR_SURV];
+    job->h_stats[3] = (int64_t)hc[CTR_NSURV];
     job->h_stats[4] = nnz;
-    job->h_stats[5] = (int64_t)hc[CTR_PAIRS];
+    job->h_stats[5] = (int64_t)hc[CTR_CAND];
     return XG_OK;
 }
 
-extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, int64_t n_t_node,
-                                const void *d_t_faces, int idx_bytes, int64_t n_t_face, int k_t,
-                                int64_t t_begin, int64_t t_end, int64_t *d_indptr, int64_t *h_nnz,
-                                void *stream, xg_overlap **job_out) {
+// d_t_ids (optional): the targets are the faces d_t_ids[t_begin .. t_end) and row i of the
+// result belongs to d_t_ids[t_begin + i]
+static int overlap_begin_impl(const xg_index *source, const double *d_t_xy, int64_t n_t_node,
+                              const void *d_t_faces, int idx_bytes, int64_t n_t_face, int k_t,
+                              const int32_t *d_t_ids, int64_t t_begin, int64_t t_end, int64_t *d_indptr,
+                              int64_t *h_nnz, void *stream, xg_overlap **job_out) {
     (void)n_t_node;
     if (!source || !job_out || !d_indptr || !h_nnz) { set_error("xg_overlap_begin: NULL argument"); return XG_ERR_INVALID; }
     *job_out = nullptr;
-    if (t_begin < 0 || t_end < t_begin || t_end > n_t_face || (idx_bytes != 4 && idx_bytes != 8)) {
+    if (t_begin < 0 || t_end < t_begin || (!d_t_ids && t_end > n_t_face) || (idx_bytes != 4 && idx_bytes != 8)) {
         set_error("xg_overlap_begin: invalid target range [%lld,%lld) of %lld", (long long)t_begin,
                   (long long)t_end, (long long)n_t_face);
         return XG_ERR_INVALID;
@@ -991,8 +1064,10 @@ extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, in
         PackedMesh pm;
         pm.perm = job->tperm.as<int32_t>(); pm.box = job->tbox.as<Box>();
         pm.poly = job->tpoly.as<double>(); pm.nvert = job->tnv.as<uint8_t>();
-        rc = pack_mesh(d_t_xy, d_t_faces, idx_bytes, t_begin, t_end, k_t, source->d_frame, nullptr, &pm, s);
+        rc = pack_mesh(d_t_xy, d_t_faces, idx_bytes, t_begin, t_end, k_t, source->d_frame, nullptr, &pm, s,
+                       nullptr, nullptr, d_t_ids);
         if (rc) goto fail;
+        // (with a face list, tperm holds list positions t_begin + i: rows stay tperm - t_begin)
 
         unsigned long long cap = (unsigned long long)n_t * PAIRS_PER_TARGET_GUESS;
         if (cap < 65536) cap = 65536;
@@ -1021,6 +1096,26 @@ fail:
     delete job;
     return rc;
 #undef OV_CUDA
+}
+
+extern "C" int xg_overlap_begin(const xg_index *source, const double *d_t_xy, int64_t n_t_node,
+                                const void *d_t_faces, int idx_bytes, int64_t n_t_face, int k_t,
+                                int64_t t_begin, int64_t t_end, int64_t *d_indptr, int64_t *h_nnz,
+                                void *stream, xg_overlap **job_out) {
+    return overlap_begin_impl(source, d_t_xy, n_t_node, d_t_faces, idx_bytes, n_t_face, k_t, nullptr, t_begin,
+                              t_end, d_indptr, h_nnz, stream, job_out);
+}
+
+extern "C" int xg_overlap_begin_ids(const xg_index *source, const double *d_t_xy, int64_t n_t_node,
+                                    const void *d_t_faces, int idx_bytes, int64_t n_t_face, int k_t,
+                                    const int32_t *d_t_ids, int64_t n_ids, int64_t *d_indptr,
+                                    int64_t *h_nnz, void *stream, xg_overlap **job_out) {
+    if (n_ids < 0 || (n_ids > 0 && !d_t_ids)) { set_error("xg_overlap_begin_ids: invalid face list"); return XG_ERR_INVALID; }
+    if (n_ids == 0)  // nothing to list: an empty range of the mesh itself
+        return overlap_begin_impl(source, d_t_xy, n_t_node, d_t_faces, idx_bytes, n_t_face, k_t, nullptr, 0, 0,
+                                  d_indptr, h_nnz, stream, job_out);
+    return overlap_begin_impl(source, d_t_xy, n_t_node, d_t_faces, idx_bytes, n_t_face, k_t, d_t_ids, 0, n_ids,
+                              d_indptr, h_nnz, stream, job_out);
 }
 
 extern "C" int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32_t *d_indices,

@@ -4,6 +4,9 @@
 
 namespace xg {
 
+// d_face_ids (optional): the faces packed are d_face_ids[f_begin .. f_end) and perm holds
+// positions in that list instead of face numbers (a rank's share of the targets when they
+// are partitioned along the space-filling curve).
 // Output arrays are caller-allocated device memory of n = f_end - f_begin
 // entries (poly: n * k * 2 doubles).
 struct PackedMesh {
@@ -23,6 +26,6 @@ struct PackedMesh {
 int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
               int64_t f_end, int k, const double *d_frame, unsigned long long *d_diag2,
               PackedMesh *out, cudaStream_t s, const double *d_clip_box = nullptr,
-              unsigned long long *d_kept = nullptr);
+              unsigned long long *d_kept = nullptr, const int32_t *d_face_ids = nullptr);
 
 }  // namespace xg

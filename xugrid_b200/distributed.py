@@ -152,3 +152,67 @@ def target_range_box(xy: torch.Tensor, faces: torch.Tensor, begin: int, end: int
                                    int(end), int(faces.shape[1]), box, _native.stream_ptr())
         )
     return (box[0], box[1], box[2], box[3])
+
+
+def curve_shard(xy: torch.Tensor, faces: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Face numbers (int32 device tensor, no particular order) of the share of ``rank`` when
+    the faces of a mesh are partitioned over ``world`` ranks along the space-filling curve
+    (``xg_target_shard``): a compact patch of the mesh whatever the caller's face numbering
+    means, where ``shard_range`` would hand a rank faces from all over the domain.  Every
+    rank computes the same cuts, so the shares are disjoint and cover the mesh."""
+    import ctypes
+
+    from . import _native
+
+    L = _native.lib()
+    n = int(faces.shape[0])
+    ids = torch.empty(n, dtype=torch.int32, device=faces.device)
+    count = ctypes.c_int64()
+    with torch.cuda.device(faces.device):
+        _native.check(
+            L.xg_target_shard(_native.ptr(xy, torch.float64), int(xy.shape[0]), _native.ptr(faces),
+                              faces.element_size(), n, int(faces.shape[1]), int(rank), int(world),
+                              _native.ptr(ids), ctypes.byref(count), _native.stream_ptr())
+        )
+    return ids[: count.value]
+
+
+def all_gather_ids(ids: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
+    """Every rank's id list: (padded (world, max_len) int32 tensor, lengths).  Done once per
+    regridder; ``scatter_gathered`` then places the outputs of every later apply."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return ids.reshape(1, -1), [int(ids.numel())]
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([ids.numel()], dtype=torch.int64, device=ids.device)
+    lens = torch.empty(world, dtype=torch.int64, device=ids.device)
+    dist.all_gather_into_tensor(lens, n_local, group=group)
+    lens = [int(v) for v in lens.tolist()]
+    pad = max(max(lens), 1)
+    send = torch.full((pad,), -1, dtype=torch.int32, device=ids.device)
+    send[: ids.numel()] = ids
+    recv = torch.empty((world, pad), dtype=torch.int32, device=ids.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv, lens
+
+
+def all_gather_by_ids(local: torch.Tensor, all_ids: torch.Tensor, lens, n_total: int,
+                      group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """``local`` is this rank's (n_extra, len(ids)) block of output columns for the faces in
+    its id list.  Returns the full (n_extra, n_total) array in the caller's face order on
+    every rank: one all_gather_into_tensor of padded slabs + one scatter through the
+    gathered id lists (``all_gather_ids``)."""
+    n_extra = int(local.shape[0])
+    world = int(all_ids.shape[0])
+    pad = int(all_ids.shape[1])
+    out = torch.full((n_extra, n_total), float("nan"), dtype=local.dtype, device=local.device)
+    if world == 1:
+        out[:, all_ids[0, : lens[0]].long()] = local
+        return out
+    send = local.new_zeros((n_extra, pad))
+    send[:, : local.shape[1]] = local
+    recv = local.new_empty((world * n_extra, pad))
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, n_extra, pad)
+    for r in range(world):
+        out[:, all_ids[r, : lens[r]].long()] = recv[r, :, : lens[r]]
+    return out

@@ -105,8 +105,21 @@ class UnstructuredGrid2d:
         return self
 
     def overlap(self, other: "UnstructuredGrid2d", relative: bool,
-                target_range: Optional[Tuple[int, int]] = None) -> MatrixCSR:
+                target_range: Optional[Tuple[int, int]] = None,
+                target_ids: Optional[torch.Tensor] = None) -> MatrixCSR:
         """unstructured.py:109-135 + sparse.py:119-127, as one device CSR."""
+        if target_ids is not None:
+            # a share of the targets given by face numbers: index only the source faces
+            # they can touch, rows in the order of the list
+            from .celltree import CellTree2d
+
+            xy, faces = other.ugrid_topology.device_arrays()
+            sxy, sfaces = self.ugrid_topology.device_arrays()
+            ids = target_ids.to(xy.device)
+            tree = CellTree2d(sxy, sfaces, -1, device=sxy.device, clip_target_ids=(xy, faces, ids))
+            self.last_tree = tree
+            indptr, indices, data = tree.intersect_faces_csr(xy, faces, -1, relative=relative, ids=ids)
+            return MatrixCSR(data, indices, indptr, int(ids.numel()), self.size, int(data.numel()))
         # the source index first: its build must not wait for target arrays that are
         # queued behind the source on the copy stream
         tree = self.ugrid_topology.celltree if target_range is None else None
@@ -149,7 +162,9 @@ class UnstructuredGrid2d:
         with ``target_range`` only for those target faces (target_index counts from its start)."""
         tree = self.ugrid_topology.celltree
         points = _target_points(other, tree.device)
-        if target_range is not None:
+        if isinstance(target_range, torch.Tensor):
+            points = points[target_range.long()].contiguous()
+        elif target_range is not None:
             points = points[target_range[0]:target_range[1]].contiguous()
         idx = tree.locate_points_device(points, tolerance)
         inside = idx != -1
@@ -172,7 +187,9 @@ class UnstructuredGrid2d:
         grid = self.ugrid_topology
         xy, faces = grid.device_arrays()
         points = _target_points(other, xy.device)
-        if target_range is not None:
+        if isinstance(target_range, torch.Tensor):
+            points = points[target_range.long()].contiguous()
+        elif target_range is not None:
             # a shard: the rows of its own target faces (the Voronoi mesh of the source is
             # replicated, like the source mesh of the overlap regridders)
             points = points[target_range[0]:target_range[1]].contiguous()
@@ -332,14 +349,27 @@ class BaseRegridder(abc.ABC):
     _TARGET_AS_POINTS = False  # True: the weights need only the target's face centroids
 
     def __init__(self, source, target, tolerance: Optional[float] = None,
-                 target_range: Optional[Tuple[int, int]] = None, sharded_upload: bool = False):
+                 target_range: Optional[Tuple[int, int]] = None, sharded_upload: bool = False,
+                 target_ids: Optional[torch.Tensor] = None):
         """``target_range=(b, e)``: this process owns only those target faces (one
-        process per GPU, see distributed.py).  ``sharded_upload=True`` (all ranks of
-        the default process group hold the same host meshes): the source mesh and the
-        target coordinates go up 1/world per rank and are replicated over NVLink."""
+        process per GPU, see distributed.py).  ``target_ids`` (int32 device tensor of
+        target face numbers, e.g. ``distributed.curve_shard``): this process owns those
+        faces; row / output column i belongs to face ``target_ids[i]``.
+        ``sharded_upload=True`` (all ranks of the default process group hold the same
+        host meshes): the source mesh and the target coordinates go up 1/world per rank
+        and are replicated over NVLink."""
         self._source = setup_grid(source)
         self._target = setup_grid(target)
         self._weights = None
+        if target_ids is not None:
+            if target_range is not None:
+                raise ValueError("give target_range or target_ids, not both")
+            if _both_structured(self._source, self._target):
+                raise NotImplementedError("target_ids is not supported for raster -> raster regridding")
+            target_ids = target_ids.to(torch.int32).contiguous()
+            # (a list of n rows: the range bookkeeping of a shard applies unchanged)
+            target_range = (0, int(target_ids.numel()))
+        self._target_ids = target_ids
         self._target_range = target_range
         if _both_structured(self._source, self._target):
             # raster -> raster: the separable path of the reference (convert_to_match,
@@ -356,9 +386,10 @@ class BaseRegridder(abc.ABC):
             self._compute_weights(self._source, self._target, tolerance)
             return
         tgt_grid = self._target.to_unstructured().ugrid_topology
-        if target_range is None:
+        if target_range is None or target_ids is not None:
             src_grid.prefetch(sharded=sharded_upload)
-            tgt_grid.prefetch(n_chunks=self._TARGET_CHUNKS if tgt_grid.n_face >= (1 << 20) else 1)
+            tgt_grid.prefetch(n_chunks=self._TARGET_CHUNKS if (tgt_grid.n_face >= (1 << 20) and target_ids is None) else 1,
+                              sharded=sharded_upload and target_ids is not None)
         else:
             # a shard: its (small) target range first, so that the clip box of the
             # source index is known while the source mesh is still arriving
@@ -519,6 +550,7 @@ class BaseRegridder(abc.ABC):
         instance._target = setup_grid(target)
         instance._source = setup_grid(_grid_from_dataset(weights, "__source"))
         instance._target_range = None
+        instance._target_ids = None
         return instance
 
     @classmethod
@@ -547,7 +579,7 @@ class CentroidLocatorRegridder(BaseRegridder):
             return
         # (a raster target is only needed as points: it is not promoted to a quad mesh)
         source_index, target_index, weight_values = source.to_unstructured().locate_centroids(
-            target, tolerance, self._target_range)
+            target, tolerance, self._target_ids if self._target_ids is not None else self._target_range)
         self._weights = MatrixCOO(weight_values, target_index.contiguous(), source_index.contiguous(),
                                   self._rows(), source.size, int(weight_values.numel()))
 
@@ -568,6 +600,8 @@ class BaseOverlapRegridder(BaseRegridder, abc.ABC):
             return
         from .distributed import all_gather_csr
 
+        if self._target_ids is not None:
+            raise NotImplementedError("gather_weights of a regridder built from a face list (target_ids)")
         self._weights = all_gather_csr(self._weights, self._target.size, group)
         self._target_range = None
 
@@ -581,7 +615,8 @@ class BaseOverlapRegridder(BaseRegridder, abc.ABC):
             self._weights = A if self._target_range is None else _csr_rows(A, *self._target_range)
             return
         src, tgt = source.to_unstructured(), target.to_unstructured()
-        self._weights = src.overlap(tgt, relative=relative, target_range=self._target_range)
+        self._weights = src.overlap(tgt, relative=relative, target_range=self._target_range,
+                                    target_ids=self._target_ids)
 
 
 class OverlapRegridder(BaseOverlapRegridder):
@@ -590,9 +625,10 @@ class OverlapRegridder(BaseOverlapRegridder):
     _METHODS = ABSOLUTE_OVERLAP_METHODS
 
     def __init__(self, source, target, method: Union[str, Callable] = "mean",
-                 target_range: Optional[Tuple[int, int]] = None, sharded_upload: bool = False):
+                 target_range: Optional[Tuple[int, int]] = None, sharded_upload: bool = False,
+                 target_ids: Optional[torch.Tensor] = None):
         super().__init__(source=source, target=target, target_range=target_range,
-                         sharded_upload=sharded_upload)
+                         sharded_upload=sharded_upload, target_ids=target_ids)
         self._setup_regrid(method)
 
     def _compute_weights(self, source, target, tolerance=None) -> None:
@@ -615,9 +651,10 @@ class RelativeOverlapRegridder(BaseOverlapRegridder):
     _METHODS = RELATIVE_OVERLAP_METHODS
 
     def __init__(self, source, target, method: Union[str, Callable] = "first_order_conservative",
-                 target_range: Optional[Tuple[int, int]] = None, sharded_upload: bool = False):
+                 target_range: Optional[Tuple[int, int]] = None, sharded_upload: bool = False,
+                 target_ids: Optional[torch.Tensor] = None):
         super().__init__(source=source, target=target, tolerance=None, target_range=target_range,
-                         sharded_upload=sharded_upload)
+                         sharded_upload=sharded_upload, target_ids=target_ids)
         self._setup_regrid(method)
 
     def _compute_weights(self, source, target, tolerance=None) -> None:
@@ -644,8 +681,8 @@ class BarycentricInterpolator(BaseRegridder):
     _TARGET_AS_POINTS = True
 
     def __init__(self, source, target, tolerance: Optional[float] = None,
-                 target_range: Optional[Tuple[int, int]] = None):
-        super().__init__(source, target, tolerance, target_range=target_range)
+                 target_range: Optional[Tuple[int, int]] = None, target_ids: Optional[torch.Tensor] = None):
+        super().__init__(source, target, tolerance, target_range=target_range, target_ids=target_ids)
         # weights of a target face sum to 1: a weighted mean also handles NaNs
         self._setup_regrid("mean")
 
@@ -658,7 +695,8 @@ class BarycentricInterpolator(BaseRegridder):
             self._weights = A if self._target_range is None else _csr_rows(A, *self._target_range)
             return
         # (a raster target is only needed as points: it is not promoted to a quad mesh)
-        self._weights = source.to_unstructured().barycentric(target, tolerance, self._target_range)
+        self._weights = source.to_unstructured().barycentric(
+            target, tolerance, self._target_ids if self._target_ids is not None else self._target_range)
 
     @classmethod
     def from_weights(cls, weights: dict, target):
@@ -725,6 +763,7 @@ class NetworkGridder(BaseRegridder):
         self._target = setup_grid(target)
         self._weights = None
         self._target_range = None
+        self._target_ids = None
         self._compute_weights(self._source, self._target, relative=False)
         self._setup_regrid(method)
 
