@@ -245,7 +245,7 @@ def run_ours(args) -> int:
     import xugrid_b200 as xb
     from xugrid_b200 import sparse
     from xugrid_b200.distributed import (all_gather_by_ids, all_gather_columns, all_gather_ids, curve_shard,
-                                         shard_range, sharded_upload)
+                                         shard_range, shared_host_array, sharded_upload)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -270,9 +270,12 @@ def run_ours(args) -> int:
     # host buffers (pinned) for the end-to-end leg
     h = {k: torch.from_numpy(v).pin_memory() for k, v in
          dict(sxy=sxy, sf=sf, txy=txy, tf=tf, values=values).items()}
-    h_out = torch.empty((1, n_t), dtype=torch.float64).pin_memory()
+    # N > 1: the result is assembled in host memory shared by the ranks; every rank copies
+    # only its own columns down, over its own PCIe link
+    h_out = shared_host_array((1, n_t), torch.float64)
     d = {k: v.to(dev) for k, v in h.items()}
-    d2h_bytes = h_out.numel() * h_out.element_size()
+    # (per rank, like h2d_bytes: the lattice workload copies only the rank's own columns down)
+    d2h_bytes = (e - b if (world > 1 and args.workload != "shuffled") else n_t) * h_out.element_size()
 
     state = {}
 
@@ -348,10 +351,10 @@ def run_ours(args) -> int:
             torch.cuda.current_stream().synchronize()
             state["e2e_out"] = h_out
         else:
+            # rank r: 1/world of the replicated arrays up (assembled over NVLink), its own
+            # target rows up, its own output columns down into the shared host array
             r = xb.OverlapRegridder(src_grid, tgt_grid, method="mean", target_range=(b, e), sharded_upload=True)
-            local = r.regrid(sharded_upload(h["values"].reshape(-1), dev).reshape(1, -1))
-            h_out.copy_(all_gather_columns(local, n_t), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            r.regrid(h["values"], out=h_out[:, b:e])
             state["e2e_out"] = h_out
 
     def timed(fn, steps, warmup):
@@ -399,6 +402,7 @@ def run_ours(args) -> int:
     check = None
     if world > 1:
         full = step(d).contiguous().clone()
+        dist.barrier()  # every rank's columns of the last end-to-end step have landed in the shared host array
         e2e_full = state["e2e_out"].to(dev) if isinstance(state.get("e2e_out"), torch.Tensor) else None
         if rank == 0:
             alone = step(d, t_range=(0, n_t), gather=False)

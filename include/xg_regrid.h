@@ -12,7 +12,7 @@
  *    Nothing throws, nothing falls back to the CPU.
  *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it.
  *    Functions that must return a size to the host synchronise that stream
- *    before returning: xg_overlap_begin (nnz), the culled index builds (number
+ *    before returning: xg_overlap_begin (nnz; xg_overlap_run does not), the culled index builds (number
  *    of faces kept), xg_intersect_edges (count), xg_face_range_bounds;
  *    xg_index_info waits for the index the first time the default tolerance
  *    is asked for.  Everything else, including xg_index_create and
@@ -154,6 +154,29 @@ int xg_overlap_begin_ids(const xg_index *source, const double *d_t_xy, int64_t n
                          void *stream, xg_overlap **job);
 int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32_t *d_indices,
                       double *d_area, int relative, void *stream);
+/* The same job enqueued in one go, WITHOUT a host round trip: the caller hands in CSR arrays
+ * sized by an upper bound (entry_cap entries; 16 per target row always suffices at comparable
+ * resolutions, see below) instead of waiting for nnz, so the host can run ahead and queue the
+ * apply and the copies behind it (the reference has no counterpart: numba code is
+ * synchronous).  d_t_ids may be NULL (targets = faces [t_begin, t_end)) or a face list
+ * (targets = d_t_ids[t_begin .. t_end)).  d_indptr receives the rows + 1 row pointers.
+ * chained != 0: d_indptr[0] already holds, ON THE DEVICE, the offset of this job's first
+ * entry -- pass the address of the last row pointer of the job before it and the jobs of
+ * consecutive target ranges fill ONE CSR matrix (how the regridders consume a target mesh
+ * that is still being uploaded range by range); chained == 0: the matrix starts at 0.
+ * Rows are written sorted by ascending source index, as by xg_overlap_finish.
+ * Nothing is waited for.  xg_overlap_result waits for the job, returns its nnz, the row
+ * pointer behind its last row and whether it is complete: a job whose candidate arena or
+ * whose caller arrays turned out too small is NOT complete (its rows are missing, nothing
+ * was written out of bounds) and must be redone with xg_overlap_begin/finish, which
+ * re-sizes.  xg_overlap_stats / _timings are valid after xg_overlap_result; release the
+ * job with xg_overlap_abort. */
+int xg_overlap_run(const xg_index *source, const double *d_t_xy, int64_t n_t_node,
+                   const void *d_t_faces, int idx_bytes, int64_t n_t_face, int k_t,
+                   const int32_t *d_t_ids, int64_t t_begin, int64_t t_end, int chained,
+                   int64_t *d_indptr, int32_t *d_indices, double *d_area, int64_t entry_cap,
+                   int relative, void *stream, xg_overlap **job);
+int xg_overlap_result(xg_overlap *job, int64_t *h_nnz, int64_t *h_nnz_end, int *h_complete);
 /* counters of the job for the byte model:
  * stats[0]=targets stats[1]=wide-node visits (V, one coalesced load of <= 32
  * boxes each) stats[2]=leaf bbox tests (C) stats[3]=pairs that passed the

@@ -32,6 +32,11 @@ def init(self, *a, **k):
     orig_init(self, *a, **k); mark("index built")
 def csr(self, *a, **k):
     r = orig_csr(self, *a, **k); mark(f"overlap rows [{k.get('t_begin')},{k.get('t_end')})"); return r
+from xugrid_b200 import sparse as _sp
+orig_apply = _sp.csr_apply
+def apply(*a, **k):
+    mark("values on device (apply starts)"); r = orig_apply(*a, **k); mark("apply done"); return r
+_sp.csr_apply = apply
 celltree.CellTree2d.__init__ = init
 celltree.CellTree2d.intersect_faces_csr = csr
 
@@ -51,5 +56,8 @@ for nchunk in chunks:
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
     print(f"--- chunks={nchunk}  wall {wall:.2f} ms")
-    for name, ev in marks[1:]:
-        print(f"  {marks[0][1].elapsed_time(ev):8.3f} ms  {name}")
+    rows = [(marks[0][1].elapsed_time(ev), name) for name, ev in marks[1:]]
+    for label, g in (("source", src), ("target", tgt)):
+        rows += [(marks[0][1].elapsed_time(ev), f"[copy stream] {label} {name}") for name, ev in getattr(g, "_upload_events", [])]
+    for t, name in sorted(rows):
+        print(f"  {t:8.3f} ms  {name}")

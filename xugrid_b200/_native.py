@@ -49,6 +49,12 @@ SIGNATURES = {
         [_vp, _vp, _i64, _vp, _int, _i64, _int, _vp, _i64, _vp, ctypes.POINTER(_i64), _vp, ctypes.POINTER(_vp)],
     ),
     "xg_overlap_finish": (_int, [_vp, _vp, _vp, _vp, _int, _vp]),
+    "xg_overlap_run": (
+        _int,
+        [_vp, _vp, _i64, _vp, _int, _i64, _int, _vp, _i64, _i64, _int, _vp, _vp, _vp, _i64, _int, _vp,
+         ctypes.POINTER(_vp)],
+    ),
+    "xg_overlap_result": (_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_int)]),
     "xg_overlap_stats": (_int, [_vp, ctypes.POINTER(_i64)]),
     "xg_overlap_timings": (_int, [_vp, ctypes.POINTER(_dbl)]),
     "xg_overlap_abort": (_int, [_vp]),

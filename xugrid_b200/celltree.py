@@ -82,6 +82,43 @@ class OverlapStats(NamedTuple):
     walks: int = 1  # full walks of the index (2 = the pair arena was too small the first time)
 
 
+class PendingOverlap:
+    """An overlap job that was enqueued without waiting (CellTree2d.intersect_faces_into)."""
+
+    def __init__(self, tree: "CellTree2d", job):
+        self._tree, self._job = tree, job
+        self._res = None
+
+    def result(self) -> Tuple[int, int, bool]:
+        """(nnz of the job, row pointer behind its last row, complete?) -- waits for the job."""
+        if self._res is None:
+            L = _native.load_library()
+            nnz, end, ok = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+            try:
+                _native.check(L.xg_overlap_result(self._job, ctypes.byref(nnz), ctypes.byref(end), ctypes.byref(ok)))
+                st = (ctypes.c_int64 * 8)()
+                _native.check(L.xg_overlap_stats(self._job, st))
+                self.stats = OverlapStats(*[int(st[i]) for i in range(7)])
+                ms = (ctypes.c_double * 8)()
+                _native.check(L.xg_overlap_timings(self._job, ms))
+                self.phase_ms = dict(zip(PHASES, [float(ms[i]) for i in range(len(PHASES))]))
+                self._tree.last_stats, self._tree.last_phase_ms = self.stats, self.phase_ms
+            finally:
+                L.xg_overlap_abort(self._job)
+                self._job = None
+            self._res = (int(nnz.value), int(end.value), bool(ok.value))
+        return self._res
+
+    def __del__(self):
+        job = getattr(self, "_job", None)
+        if job is not None and job.value:
+            try:
+                _native.load_library().xg_overlap_abort(job)
+            except Exception:
+                pass
+            self._job = None
+
+
 class CellTree2d:
     def __init__(self, vertices: ArrayLike, faces: ArrayLike, fill_value: int = -1, device=None,
                  clip_box=None, clip_targets=None, clip_target_ids=None):
@@ -239,6 +276,50 @@ class CellTree2d:
                 )
             )
         return indptr, indices, area
+
+    def intersect_faces_into(
+        self,
+        vertices: torch.Tensor,
+        faces: torch.Tensor,
+        indptr: torch.Tensor,
+        indices: torch.Tensor,
+        area: torch.Tensor,
+        t_begin: int = 0,
+        t_end: Optional[int] = None,
+        relative: bool = False,
+        ids: Optional[torch.Tensor] = None,
+        chained: bool = False,
+    ) -> "PendingOverlap":
+        """
+        The same CSR rows written into arrays the caller sized by an upper bound, with
+        NOTHING waited for (``xg_overlap_run``): ``indptr`` is the (rows + 1) slice of the
+        row pointer these target rows own, ``indices`` / ``area`` the whole entry arrays.
+        ``chained=True``: ``indptr[0]`` already holds (on the device) the offset of the first
+        entry, i.e. the last row pointer of the rows before -- consecutive target ranges
+        fill one matrix.  Returns a handle; ``.result()`` waits and tells whether the job
+        is complete (arena and arrays were large enough).
+        """
+        L = _native.lib()
+        with torch.cuda.device(self.device):
+            n_t, k_t = int(faces.shape[0]), int(faces.shape[1])
+            if t_end is None:
+                t_end = n_t
+            if ids is not None:
+                t_begin, t_end = 0, int(ids.numel())
+            rows = t_end - t_begin
+            if indptr.numel() != rows + 1 or indices.numel() != area.numel():
+                raise ValueError("indptr must have rows + 1 entries; indices and area the same capacity")
+            job = ctypes.c_void_p()
+            _native.check(
+                L.xg_overlap_run(
+                    self._h, _native.ptr(vertices, torch.float64), int(vertices.shape[0]), _native.ptr(faces),
+                    faces.element_size(), n_t, k_t, _native.ptr(ids, torch.int32) if ids is not None else None,
+                    t_begin, t_end, 1 if chained else 0, _native.ptr(indptr, torch.int64),
+                    _native.ptr(indices, torch.int32), _native.ptr(area, torch.float64), int(area.numel()),
+                    1 if relative else 0, _native.stream_ptr(), ctypes.byref(job),
+                )
+            )
+        return PendingOverlap(self, job)
 
     def intersect_faces(self, vertices: ArrayLike, faces: ArrayLike, fill_value: int = -1):
         """numba_celltree-compatible triplets: (face index of the query mesh

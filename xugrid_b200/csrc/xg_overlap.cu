@@ -49,7 +49,11 @@ constexpr int PAIRS_PER_TARGET_GUESS = 16;
 // device counters of one job
 // CTR_PAIRS / CTR_SURV count arena SLOTS (reserved windows, unused tails included);
 // CTR_CAND / CTR_NSURV the candidate pairs / survivors themselves
-enum { CTR_VISITS = 0, CTR_TESTS = 1, CTR_PAIRS = 2, CTR_SURV = 3, CTR_CAND = 4, CTR_HUGE = 5, CTR_LONG = 6, CTR_NSURV = 7, CTR_N = 8 };
+// CTR_BASE: offset of the job's first CSR entry (0, or the last row pointer of the job before
+// it when jobs are chained); CTR_NNZ_END: row pointer behind the job's last row;
+// CTR_FLAGS: bit 0 = an entry would have landed beyond the caller's arrays
+enum { CTR_VISITS = 0, CTR_TESTS = 1, CTR_PAIRS = 2, CTR_SURV = 3, CTR_CAND = 4, CTR_HUGE = 5, CTR_LONG = 6, CTR_NSURV = 7,
+       CTR_BASE = 8, CTR_NNZ_END = 9, CTR_FLAGS = 10, CTR_N = 12 };
 
 struct TraverseParams {
     const Box *boxes[MAX_LEVELS + 1];  // [0] = leaves, [d] = node level d-1
@@ -641,6 +645,9 @@ struct RowMove {
     const int64_t *indptr;     // caller's row pointer
     int32_t *indices;
     double *data;
+    int64_t entry_cap;         // entries the caller's arrays can hold (rows beyond it are dropped and flagged)
+    unsigned long long *flags;
+    __device__ __forceinline__ bool fits(int64_t dst, int64_t n) const { return dst + n <= entry_cap; }
 };
 
 __device__ __forceinline__ double entry_value(const RowMove &R, int32_t s, double a) {
@@ -688,11 +695,13 @@ k_move_rows(const RowMove R, int64_t n_t, int32_t *__restrict__ long_rows,
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t src = 0, dst = 0;
     int n = 0;
+    if (*R.flags != 0ull) return;  // (the rows do not fit the caller's arrays: nothing is moved)
     if (t < n_t) {
         n = R.fill_cnt[t];
         src = R.prov_ptr[t];
         dst = R.indptr[R.tperm[t] - R.t_begin];
     }
+    if (n > 0 && !R.fits(dst, n)) n = 0;
     const bool is_long = n > SORT_SHORT;
     const unsigned lm = __ballot_sync(0xffffffffu, is_long);
     if (lm) {
@@ -727,6 +736,7 @@ k_move_long_rows(const RowMove R, const int32_t *__restrict__ long_rows,
         const int64_t n = R.fill_cnt[t];
         const int64_t src = R.prov_ptr[t];
         const int64_t dst = R.indptr[R.tperm[t] - R.t_begin];
+        // (rows that do not fit the caller's arrays never get here: k_move_rows dropped them)
         if (n <= SORT_LONG_CAP) {
             for (int i = lane; i < n; i += 32) {
                 int32_t s;
@@ -861,8 +871,27 @@ struct xg_overlap {
     cudaEvent_t ev[XG_N_PHASES + 1];
     int n_ev = 0;
     double h_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // the attempt in flight: arena capacity, and (after overlap_collect) what the device reported
+    unsigned long long cap = 0, needed = 0, flags = 0;
+    int64_t nnz_end = 0;
+    double *h_ctr = nullptr;     // pinned slot the counters are copied to
+    // xg_overlap_run: nothing is waited for until xg_overlap_result
+    bool deferred = false, empty = false;
+    cudaEvent_t done = nullptr;
     xg_overlap() { for (int i = 0; i <= XG_N_PHASES; ++i) ev[i] = nullptr; }
-    ~xg_overlap() { for (int i = 0; i <= XG_N_PHASES; ++i) if (ev[i]) cudaEventDestroy(ev[i]); }
+    ~xg_overlap() {
+        for (int i = 0; i <= XG_N_PHASES; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+        if (done) {
+            // (the pinned slot may still be the target of the counter copy)
+            if (h_ctr && !stats_valid) cudaEventSynchronize(done);
+            cudaEventDestroy(done);
+        }
+        if (h_ctr) pinned_slot_release(h_ctr);
+    }
+    void release_scratch() {
+        tperm.release(); tbox.release(); tpoly.release(); tnv.release(); pairs.release(); surv.release();
+        prov_col.release(); cnt.release(); prov_ptr.release(); scan_tmp.release(); ctr.release();
+    }
     cudaError_t mark() {
         if (!ev[n_ev]) {
             cudaError_t e = cudaEventCreate(&ev[n_ev]);
@@ -915,17 +944,28 @@ static int estimate_candidates(xg_overlap *job, unsigned long long *estimate) {
     return XG_OK;
 }
 
-// one attempt with a pair arena of `cap` entries; *needed receives the number of
-// candidate pairs the walk found (> cap means: run again with that capacity)
-static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_indptr,
-                           unsigned long long *needed) {
+// dst[0 .. n) = *src (rows of an empty job all point at the job's first entry)
+__global__ void __launch_bounds__(256)
+k_fill_from(int64_t *__restrict__ dst, int64_t n, const int64_t *__restrict__ src) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = *src;
+}
+
+// Enqueues one attempt with a pair arena of `cap` entries: walk, filter, clip, row pointer.
+// Nothing is read back.  chained: the job's first entry sits at the offset found in
+// d_indptr[0] on the device (the last row pointer of the job before it) instead of 0.
+static int overlap_enqueue(xg_overlap *job, unsigned long long cap, int64_t *d_indptr, bool chained) {
     const xg_index *source = job->src;
     cudaStream_t s = job->s;
     const int64_t n_t = job->n_t;
     const int k_t = job->k_t, ks = source->k;
     job->n_ev = 1;  // keep ev[0] (pack start), re-record the rest
+    job->cap = cap;
 
     XG_CUDA(cudaMemsetAsync(job->ctr.p, 0, sizeof(unsigned long long) * CTR_N, s));
+    if (chained)
+        XG_CUDA(cudaMemcpyAsync(job->ctr.as<unsigned long long>() + CTR_BASE, d_indptr, sizeof(int64_t),
+                                cudaMemcpyDeviceToDevice, s));
     XG_CUDA(job->pairs.alloc(sizeof(int2) * (size_t)cap, s));
     // (+ the unused tails of the last survivor windows: at most 8 blocks of 8 warps per SM)
     XG_CUDA(job->surv.alloc(sizeof(int2) * ((size_t)cap + (size_t)NUM_SMS * 64 * SAT_WIN), s));
@@ -980,38 +1020,168 @@ static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_i
                                                                n_t, row_cnt);
     XG_CHECK_LAUNCH();
     {
+        // row pointer in the caller's row order, starting at the job's base offset (a value
+        // that is only known on the device when jobs are chained)
         cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(row_cnt, CastI64());
+        cub::FutureValue<int64_t> base(job->ctr.as<int64_t>() + CTR_BASE);  // (iterator type int64_t*: any other would be read on the HOST through operator T())
         size_t tb = job->scan_tmp_bytes;
-        XG_CUDA(cub::DeviceScan::ExclusiveSum(job->scan_tmp.p, tb, it, d_indptr, n_t + 1, s));
+        XG_CUDA(cub::DeviceScan::ExclusiveScan(job->scan_tmp.p, tb, it, d_indptr, cub::Sum(), base, n_t + 1, s));
     }
-    // the one host round trip of a job: nnz sizes the caller's arrays.  Read-backs go through
-    // a pinned slot (a pageable destination would make the copies synchronous one by one)
-    int64_t nnz = 0;
+    XG_CUDA(cudaMemcpyAsync(job->ctr.as<unsigned long long>() + CTR_NNZ_END, d_indptr + n_t, sizeof(int64_t),
+                            cudaMemcpyDeviceToDevice, s));
+    return XG_OK;
+}
+
+// the counters of the attempt into a pinned host slot (asynchronous), then the end mark
+static int overlap_request_counters(xg_overlap *job) {
+    if (!job->h_ctr) {
+        job->h_ctr = pinned_slot_acquire();
+        if (!job->h_ctr) { set_error("overlap: no pinned host memory"); return XG_ERR_NOMEM; }
+    }
+    static_assert(sizeof(unsigned long long) * CTR_N <= 128, "a pinned slot holds 128 bytes");
+    XG_CUDA(cudaMemcpyAsync(job->h_ctr, job->ctr.p, sizeof(unsigned long long) * CTR_N, cudaMemcpyDeviceToHost, job->s));
+    XG_CUDA(job->mark());  // end
+    return XG_OK;
+}
+
+// host side of a finished attempt (the stream has been synchronised behind
+// overlap_request_counters): counters -> job
+static void overlap_collect(xg_overlap *job) {
     unsigned long long hc[CTR_N];
-    {
-        double *slot = pinned_slot_acquire();
-        if (!slot) { set_error("overlap: no pinned host memory"); return XG_ERR_NOMEM; }
-        cudaError_t e = cudaMemcpyAsync(slot, d_indptr + n_t, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(slot + 1, job->ctr.p, sizeof(hc), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = job->mark();  // end
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        memcpy(&nnz, slot, sizeof(nnz));
-        memcpy(hc, slot + 1, sizeof(hc));
-        pinned_slot_release(slot);
-        if (e != cudaSuccess) return cuda_fail(e, "overlap read-back", __FILE__, __LINE__);
-    }
-    *needed = hc[CTR_PAIRS];
-    if (hc[CTR_PAIRS] > cap) return XG_OK;  // caller re-runs
+    memcpy(hc, job->h_ctr, sizeof(hc));
+    job->needed = hc[CTR_PAIRS];
+    job->flags = hc[CTR_FLAGS];
     job->collect();
-    job->nnz = nnz;
+    job->nnz = (int64_t)hc[CTR_NNZ_END] - (int64_t)hc[CTR_BASE];
+    job->nnz_end = (int64_t)hc[CTR_NNZ_END];
     job->n_cand = (int64_t)hc[CTR_CAND];
     job->n_surv = (int64_t)hc[CTR_NSURV];
-    job->h_stats[0] = n_t;
+    job->h_stats[0] = job->n_t;
     job->h_stats[1] = (int64_t)hc[CTR_VISITS];
     job->h_stats[2] = (int64_t)hc[CTR_TESTS];
     job->h_stats[3] = (int64_t)hc[CTR_NSURV];
-    job->h_stats[4] = nnz;
+    job->h_stats[4] = job->nnz;
     job->h_stats[5] = (int64_t)hc[CTR_CAND];
+}
+
+// one attempt with a pair arena of `cap` entries, waited for; *needed receives the number
+// of arena slots the walk wanted (> cap means: run again with that capacity)
+static int overlap_attempt(xg_overlap *job, unsigned long long cap, int64_t *d_indptr,
+                           unsigned long long *needed) {
+    int rc = overlap_enqueue(job, cap, d_indptr, false);
+    if (rc) return rc;
+    // the one host round trip of a job: nnz sizes the caller's arrays.  Read-backs go through
+    // a pinned slot (a pageable destination would make the copies synchronous one by one)
+    rc = overlap_request_counters(job);
+    if (rc) return rc;
+    XG_CUDA(cudaStreamSynchronize(job->s));
+    overlap_collect(job);
+    *needed = job->needed;
+    return XG_OK;
+}
+
+// xg_overlap_run: the caller's arrays were sized by an upper bound.  If the rows do not fit
+// (ctr[CTR_NNZ_END] is the exact end), the job flags itself, moves nothing and -- so that an
+// apply already queued behind it reads empty rows instead of unwritten entries --
+// k_void_rows points every row at the job's first entry.
+__global__ void k_check_capacity(unsigned long long *__restrict__ ctr, int64_t entry_cap) {
+    if ((int64_t)ctr[CTR_NNZ_END] > entry_cap) ctr[CTR_FLAGS] |= 1ull;
+}
+__global__ void __launch_bounds__(256)
+k_void_rows(int64_t *__restrict__ indptr, int64_t n_t, const unsigned long long *__restrict__ ctr) {
+    if (ctr[CTR_FLAGS] == 0ull) return;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_t) indptr[i + 1] = (int64_t)ctr[CTR_BASE];
+}
+
+// provisional rows -> the caller's CSR arrays (xg_overlap_finish / xg_overlap_run)
+static int enqueue_move_rows(xg_overlap *job, const int64_t *d_indptr, int32_t *d_indices, double *d_area,
+                             int64_t entry_cap, int relative, cudaStream_t s) {
+    const xg_index *src = job->src;
+    RowMove R;
+    int32_t *cand_cnt = job->cnt.as<int32_t>();
+    R.prov_ptr = job->prov_ptr.as<int64_t>(); R.fill_cnt = cand_cnt + (job->n_t + 1);
+    R.prov_col = job->prov_col.as<int32_t>(); R.prov_val = job->pairs.as<double>();
+    R.tperm = job->tperm.as<int32_t>(); R.t_begin = job->t_begin;
+    R.sperm = src->perm; R.spoly = (const double2 *)src->poly; R.snv = src->nvert; R.ks = src->k;
+    R.relative = relative; R.indptr = d_indptr; R.indices = d_indices; R.data = d_area;
+    R.entry_cap = entry_cap; R.flags = job->ctr.as<unsigned long long>() + CTR_FLAGS;
+    if (entry_cap != INT64_MAX) {
+        k_check_capacity<<<1, 1, 0, s>>>(job->ctr.as<unsigned long long>(), entry_cap);
+        XG_CHECK_LAUNCH();
+    }
+    // rows longer than SORT_SHORT are queued in the (now dead) target box buffer
+    unsigned long long *n_long = job->ctr.as<unsigned long long>() + CTR_LONG;
+    int32_t *long_rows = job->tbox.as<int32_t>();
+    k_move_rows<<<(unsigned)div_up(job->n_t, 256), 256, 0, s>>>(R, job->n_t, long_rows, n_long);
+    unsigned long long *n_huge = job->ctr.as<unsigned long long>() + CTR_HUGE;
+    int32_t *huge_rows = long_rows + job->n_t;  // second n_t ints of the same 32 * n_t byte buffer
+    k_move_long_rows<<<NUM_SMS * 4, 128, 0, s>>>(R, long_rows, n_long, huge_rows, n_huge);
+    k_move_huge_rows<<<NUM_SMS, 1024, 0, s>>>(R, huge_rows, n_huge);
+    XG_CHECK_LAUNCH();
+    if (entry_cap != INT64_MAX) {
+        k_void_rows<<<(unsigned)div_up(job->n_t, 256), 256, 0, s>>>(const_cast<int64_t *>(d_indptr), job->n_t,
+                                                                  job->ctr.as<unsigned long long>());
+        XG_CHECK_LAUNCH();
+    }
+    return XG_OK;
+}
+
+// buffers every attempt needs + the packed targets; returns the default arena capacity
+static int overlap_prepare(xg_overlap *job, const double *d_t_xy, const void *d_t_faces, int idx_bytes,
+                           const int32_t *d_t_ids, int64_t t_begin, int64_t t_end, unsigned long long *cap_out) {
+    const xg_index *source = job->src;
+    cudaStream_t s = job->s;
+    const int64_t n_t = job->n_t;
+    const int k_t = job->k_t;
+    XG_CUDA(job->mark());  // XG_PHASE_PACK
+    XG_CUDA(job->ctr.alloc(sizeof(unsigned long long) * CTR_N, s));
+    XG_CUDA(job->tperm.alloc(sizeof(int32_t) * (size_t)n_t, s));
+    XG_CUDA(job->tbox.alloc(sizeof(Box) * (size_t)n_t, s));
+    XG_CUDA(job->tpoly.alloc(sizeof(double) * 2 * (size_t)k_t * (size_t)n_t, s));
+    XG_CUDA(job->tnv.alloc((size_t)n_t, s));
+    XG_CUDA(job->cnt.alloc(sizeof(int32_t) * 3 * (size_t)(n_t + 1), s));
+    XG_CUDA(job->prov_ptr.alloc(sizeof(int64_t) * (size_t)(n_t + 1), s));
+    {
+        // one scratch buffer serves both scans of an attempt
+        cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(job->cnt.as<int32_t>(), CastI64());
+        size_t tb_sum = 0, tb_scan = 0;
+        XG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb_sum, it, job->prov_ptr.as<int64_t>(), n_t + 1, s));
+        cub::FutureValue<int64_t> base(job->ctr.as<int64_t>() + CTR_BASE);  // (iterator type int64_t*: any other would be read on the HOST through operator T())
+        XG_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tb_scan, it, job->prov_ptr.as<int64_t>(), cub::Sum(), base,
+                                               n_t + 1, s));
+        job->scan_tmp_bytes = tb_sum > tb_scan ? tb_sum : tb_scan;
+        XG_CUDA(job->scan_tmp.alloc(job->scan_tmp_bytes, s));
+    }
+    PackedMesh pm;
+    pm.perm = job->tperm.as<int32_t>(); pm.box = job->tbox.as<Box>();
+    pm.poly = job->tpoly.as<double>(); pm.nvert = job->tnv.as<uint8_t>();
+    int rc = pack_mesh(d_t_xy, d_t_faces, idx_bytes, t_begin, t_end, k_t, source->d_frame, nullptr, &pm, s,
+                       nullptr, nullptr, d_t_ids);
+    if (rc) return rc;
+    // (with a face list, tperm holds list positions t_begin + i: rows stay tperm - t_begin)
+
+    unsigned long long cap = (unsigned long long)n_t * PAIRS_PER_TARGET_GUESS;
+    if (cap < 65536) cap = 65536;
+    if (source->n_face > 2 * n_t && n_t >= 32 * SAMPLE_STRIDE * 8) {
+        unsigned long long est = 0;
+        rc = estimate_candidates(job, &est);  // (one host round trip)
+        if (rc) return rc;
+        if (est > cap) cap = est;
+    }
+    *cap_out = cap;
+    return XG_OK;
+}
+
+static int overlap_check_args(const char *who, const xg_index *source, const void *d_indptr, const int32_t *d_t_ids,
+                              int idx_bytes, int64_t n_t_face, int k_t, int64_t t_begin, int64_t t_end) {
+    if (!source || !d_indptr) { set_error("%s: NULL argument", who); return XG_ERR_INVALID; }
+    if (t_begin < 0 || t_end < t_begin || (!d_t_ids && t_end > n_t_face) || (idx_bytes != 4 && idx_bytes != 8)) {
+        set_error("%s: invalid target range [%lld,%lld) of %lld", who, (long long)t_begin, (long long)t_end,
+                  (long long)n_t_face);
+        return XG_ERR_INVALID;
+    }
+    if (k_t < 3 || k_t > XG_MAX_N_VERTEX) { set_error("%s: unsupported k_t=%d", who, k_t); return XG_ERR_UNSUPPORTED; }
     return XG_OK;
 }
 
@@ -1022,20 +1192,15 @@ static int overlap_begin_impl(const xg_index *source, const double *d_t_xy, int6
                               const int32_t *d_t_ids, int64_t t_begin, int64_t t_end, int64_t *d_indptr,
                               int64_t *h_nnz, void *stream, xg_overlap **job_out) {
     (void)n_t_node;
-    if (!source || !job_out || !d_indptr || !h_nnz) { set_error("xg_overlap_begin: NULL argument"); return XG_ERR_INVALID; }
+    if (!job_out || !h_nnz) { set_error("xg_overlap_begin: NULL argument"); return XG_ERR_INVALID; }
     *job_out = nullptr;
-    if (t_begin < 0 || t_end < t_begin || (!d_t_ids && t_end > n_t_face) || (idx_bytes != 4 && idx_bytes != 8)) {
-        set_error("xg_overlap_begin: invalid target range [%lld,%lld) of %lld", (long long)t_begin,
-                  (long long)t_end, (long long)n_t_face);
-        return XG_ERR_INVALID;
-    }
-    if (k_t < 3 || k_t > XG_MAX_N_VERTEX) { set_error("xg_overlap_begin: unsupported k_t=%d", k_t); return XG_ERR_UNSUPPORTED; }
+    int rc = overlap_check_args("xg_overlap_begin", source, d_indptr, d_t_ids, idx_bytes, n_t_face, k_t, t_begin, t_end);
+    if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     index_note_use(source, s);
     const int64_t n_t = t_end - t_begin;
     xg_overlap *job = new xg_overlap();
     job->src = source; job->t_begin = t_begin; job->n_t = n_t; job->k_t = k_t; job->s = s;
-    int rc = XG_OK;
 #define OV_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = cuda_fail(e__, #call, __FILE__, __LINE__); goto fail; } } while (0)
     {
         if (n_t == 0 || source->n_face == 0) {
@@ -1047,36 +1212,9 @@ static int overlap_begin_impl(const xg_index *source, const double *d_t_xy, int6
             *job_out = job;
             return XG_OK;
         }
-        OV_CUDA(job->mark());  // XG_PHASE_PACK
-        OV_CUDA(job->ctr.alloc(sizeof(unsigned long long) * CTR_N, s));
-        OV_CUDA(job->tperm.alloc(sizeof(int32_t) * (size_t)n_t, s));
-        OV_CUDA(job->tbox.alloc(sizeof(Box) * (size_t)n_t, s));
-        OV_CUDA(job->tpoly.alloc(sizeof(double) * 2 * (size_t)k_t * (size_t)n_t, s));
-        OV_CUDA(job->tnv.alloc((size_t)n_t, s));
-        OV_CUDA(job->cnt.alloc(sizeof(int32_t) * 3 * (size_t)(n_t + 1), s));
-        OV_CUDA(job->prov_ptr.alloc(sizeof(int64_t) * (size_t)(n_t + 1), s));
-        {
-            cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(job->cnt.as<int32_t>(), CastI64());
-            OV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, job->scan_tmp_bytes, it, job->prov_ptr.as<int64_t>(),
-                                                  n_t + 1, s));
-            OV_CUDA(job->scan_tmp.alloc(job->scan_tmp_bytes, s));
-        }
-        PackedMesh pm;
-        pm.perm = job->tperm.as<int32_t>(); pm.box = job->tbox.as<Box>();
-        pm.poly = job->tpoly.as<double>(); pm.nvert = job->tnv.as<uint8_t>();
-        rc = pack_mesh(d_t_xy, d_t_faces, idx_bytes, t_begin, t_end, k_t, source->d_frame, nullptr, &pm, s,
-                       nullptr, nullptr, d_t_ids);
+        unsigned long long cap = 0;
+        rc = overlap_prepare(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, t_begin, t_end, &cap);
         if (rc) goto fail;
-        // (with a face list, tperm holds list positions t_begin + i: rows stay tperm - t_begin)
-
-        unsigned long long cap = (unsigned long long)n_t * PAIRS_PER_TARGET_GUESS;
-        if (cap < 65536) cap = 65536;
-        if (source->n_face > 2 * n_t && n_t >= 32 * SAMPLE_STRIDE * 8) {
-            unsigned long long est = 0;
-            rc = estimate_candidates(job, &est);
-            if (rc) goto fail;
-            if (est > cap) cap = est;
-        }
         unsigned long long needed = 0;
         rc = overlap_attempt(job, cap, d_indptr, &needed);
         if (rc) goto fail;
@@ -1125,29 +1263,85 @@ extern "C" int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32
     int rc = XG_OK;
     if (job->nnz > 0) {
         if (!d_indices || !d_area || !d_indptr) { set_error("xg_overlap_finish: NULL output"); delete job; return XG_ERR_INVALID; }
-        const xg_index *src = job->src;
-        RowMove R;
-        int32_t *cand_cnt = job->cnt.as<int32_t>();
-        R.prov_ptr = job->prov_ptr.as<int64_t>(); R.fill_cnt = cand_cnt + (job->n_t + 1);
-        R.prov_col = job->prov_col.as<int32_t>(); R.prov_val = job->pairs.as<double>();
-        R.tperm = job->tperm.as<int32_t>(); R.t_begin = job->t_begin;
-        R.sperm = src->perm; R.spoly = (const double2 *)src->poly; R.snv = src->nvert; R.ks = src->k;
-        R.relative = relative; R.indptr = d_indptr; R.indices = d_indices; R.data = d_area;
-        // rows longer than SORT_SHORT are queued in the (now dead) target box buffer
-        unsigned long long *n_long = job->ctr.as<unsigned long long>() + CTR_LONG;
-        int32_t *long_rows = job->tbox.as<int32_t>();
-        k_move_rows<<<(unsigned)div_up(job->n_t, 256), 256, 0, s>>>(R, job->n_t, long_rows, n_long);
-        unsigned long long *n_huge = job->ctr.as<unsigned long long>() + CTR_HUGE;
-        int32_t *huge_rows = long_rows + job->n_t;  // second n_t ints of the same 32 * n_t byte buffer
-        k_move_long_rows<<<NUM_SMS * 4, 128, 0, s>>>(R, long_rows, n_long, huge_rows, n_huge);
-        k_move_huge_rows<<<NUM_SMS, 1024, 0, s>>>(R, huge_rows, n_huge);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) rc = cuda_fail(e, "k_move_rows", __FILE__, __LINE__);
+        rc = enqueue_move_rows(job, d_indptr, d_indices, d_area, INT64_MAX, relative, s);
     }
     // buffers are released stream-ordered on the stream that produced them
     if (s != job->s) cudaStreamSynchronize(s);
     delete job;
     return rc;
+}
+
+// The whole job enqueued at once: no host round trip between the walk and the caller's
+// CSR arrays, which are sized by an upper bound instead of the nnz read-back.
+extern "C" int xg_overlap_run(const xg_index *source, const double *d_t_xy, int64_t n_t_node,
+                              const void *d_t_faces, int idx_bytes, int64_t n_t_face, int k_t,
+                              const int32_t *d_t_ids, int64_t t_begin, int64_t t_end, int chained,
+                              int64_t *d_indptr, int32_t *d_indices, double *d_area, int64_t entry_cap,
+                              int relative, void *stream, xg_overlap **job_out) {
+    (void)n_t_node;
+    if (!job_out || !d_indices || !d_area || entry_cap < 0) { set_error("xg_overlap_run: invalid argument"); return XG_ERR_INVALID; }
+    *job_out = nullptr;
+    int rc = overlap_check_args("xg_overlap_run", source, d_indptr, d_t_ids, idx_bytes, n_t_face, k_t, t_begin, t_end);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    index_note_use(source, s);
+    const int64_t n_t = t_end - t_begin;
+    xg_overlap *job = new xg_overlap();
+    job->src = source; job->t_begin = t_begin; job->n_t = n_t; job->k_t = k_t; job->s = s;
+    job->deferred = true;
+    job->h_stats[0] = n_t;
+    job->h_stats[6] = 1;
+    auto fail = [&](int code) { delete job; return code; };
+    if (n_t == 0 || source->n_face == 0) {
+        // every row is empty: all row pointers = the job's first entry
+        cudaError_t e = cudaSuccess;
+        if (!chained) e = cudaMemsetAsync(d_indptr, 0, sizeof(int64_t) * (size_t)(n_t + 1), s);
+        else if (n_t > 0) {
+            k_fill_from<<<(unsigned)div_up(n_t, 256), 256, 0, s>>>(d_indptr + 1, n_t, d_indptr);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) return fail(cuda_fail(e, "xg_overlap_run (empty job)", __FILE__, __LINE__));
+        job->empty = true;
+        *job_out = job;
+        return XG_OK;
+    }
+    unsigned long long cap = 0;
+    rc = overlap_prepare(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, t_begin, t_end, &cap);
+    if (rc) return fail(rc);
+    rc = overlap_enqueue(job, cap, d_indptr, chained != 0);
+    if (rc) return fail(rc);
+    rc = enqueue_move_rows(job, d_indptr, d_indices, d_area, entry_cap, relative, s);
+    if (rc) return fail(rc);
+    rc = overlap_request_counters(job);
+    if (rc) return fail(rc);
+    {
+        cudaError_t e = cudaEventCreateWithFlags(&job->done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(job->done, s);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "xg_overlap_run (event)", __FILE__, __LINE__));
+    }
+    // the scratch goes back to the block cache in stream order: the job that follows on
+    // this stream re-uses it while the host is still far ahead
+    job->release_scratch();
+    *job_out = job;
+    return XG_OK;
+}
+
+extern "C" int xg_overlap_result(xg_overlap *job, int64_t *h_nnz, int64_t *h_nnz_end, int *h_complete) {
+    if (!job || !job->deferred) { set_error("xg_overlap_result: not a job of xg_overlap_run"); return XG_ERR_INVALID; }
+    if (!job->stats_valid) {
+        if (!job->empty) {
+            XG_CUDA(cudaEventSynchronize(job->done));
+            overlap_collect(job);
+        }
+        job->stats_valid = true;
+    }
+    // incomplete: the pair arena was too small (nothing was written) or rows did not fit
+    // the caller's arrays; the caller runs the job again through xg_overlap_begin
+    const bool complete = job->empty || (job->needed <= job->cap && job->flags == 0);
+    if (h_nnz) *h_nnz = job->nnz;
+    if (h_nnz_end) *h_nnz_end = job->nnz_end;
+    if (h_complete) *h_complete = complete ? 1 : 0;
+    return XG_OK;
 }
 
 extern "C" int xg_overlap_stats(const xg_overlap *job, int64_t stats[8]) {

@@ -145,8 +145,9 @@ class Ugrid2d:
             with torch.cuda.stream(copy_stream):
                 self._xy_d = sharded_upload(self._xy_pin, dev)
                 self._faces_d = sharded_upload(self._faces_pin, dev)
-                self._xy_ready = torch.cuda.Event()
+                self._xy_ready = torch.cuda.Event(enable_timing=True)
                 self._xy_ready.record(copy_stream)
+                self._upload_events = [("mesh replicated", self._xy_ready)]
                 self._chunks = [(0, n, self._xy_ready)]
                 self._ready = self._xy_ready
                 self._face_range = None
@@ -166,15 +167,18 @@ class Ugrid2d:
                 self._xy_d = sharded_upload(self._xy_pin, dev)
             else:
                 self._xy_d = self._xy_pin.to(dev, non_blocking=True)
-            self._xy_ready = torch.cuda.Event()
+            self._xy_ready = torch.cuda.Event(enable_timing=True)
             self._xy_ready.record(copy_stream)
+            # (name, event) of every upload milestone, for scripts/e2e_timeline.py
+            self._upload_events = [("coordinates uploaded", self._xy_ready)]
             self._faces_d = torch.empty(self._faces_pin.shape, dtype=self._faces_pin.dtype, device=dev)
             self._chunks = []
             for b, e in zip(bounds[:-1], bounds[1:]):
                 self._faces_d[b:e].copy_(self._faces_pin[b:e], non_blocking=True)
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=True)
                 ev.record(copy_stream)
                 self._chunks.append((b, e, ev))
+                self._upload_events.append((f"faces [{b},{e}) uploaded", ev))
             self._ready = self._chunks[-1][2] if self._chunks else self._xy_ready
             self._face_range = None if (fb, fe) == (0, n) else (fb, fe)
 

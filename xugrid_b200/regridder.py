@@ -104,10 +104,23 @@ class UnstructuredGrid2d:
     def to_unstructured(self) -> "UnstructuredGrid2d":
         return self
 
+    # candidate pairs per target row the deferred path sizes its arrays for (what the
+    # library's own pair arena holds by default: a job that needs more is redone)
+    _ENTRIES_PER_ROW = 16
+
     def overlap(self, other: "UnstructuredGrid2d", relative: bool,
                 target_range: Optional[Tuple[int, int]] = None,
-                target_ids: Optional[torch.Tensor] = None) -> MatrixCSR:
-        """unstructured.py:109-135 + sparse.py:119-127, as one device CSR."""
+                target_ids: Optional[torch.Tensor] = None, deferred: bool = False):
+        """unstructured.py:109-135 + sparse.py:119-127, as one device CSR.
+        ``deferred=True``: nothing is waited for (``sparse.PendingCSR``): the arrays are
+        sized by an upper bound and the jobs of a target mesh that is still arriving in
+        face ranges are chained on the device."""
+        if deferred:
+            rows = (other.size if target_range is None else target_range[1] - target_range[0]) \
+                if target_ids is None else int(target_ids.numel())
+            # (a source much finer than the targets needs a sampled arena size: waiting path)
+            if rows > 0 and self.size <= 2 * rows:
+                return self._overlap_deferred(other, relative, target_range, target_ids, rows)
         if target_ids is not None:
             # a share of the targets given by face numbers: index only the source faces
             # they can touch, rows in the order of the list
@@ -155,6 +168,49 @@ class UnstructuredGrid2d:
             xy, faces, -1, t_begin=t_begin, t_end=t_end, relative=relative
         )
         return MatrixCSR(data, indices, indptr, t_end - t_begin, self.size, int(data.numel()))
+
+    def _overlap_deferred(self, other, relative, target_range, target_ids, rows: int):
+        from .celltree import CellTree2d
+
+        tgt = other.ugrid_topology
+        tree = self.ugrid_topology.celltree if (target_range is None and target_ids is None) else None
+        chunks = tgt.device_chunks() if (target_range is None and target_ids is None) else None
+        if chunks is not None:
+            xy, faces, ranges = chunks
+        elif target_ids is not None:
+            xy, faces = tgt.device_arrays()
+            ranges = None
+        else:
+            t_begin, t_end = (0, other.size) if target_range is None else target_range
+            xy, faces = tgt.device_arrays(face_range=(t_begin, t_end))
+            ranges = [(t_begin, t_end)]
+        dev = xy.device
+        if tree is None:
+            sxy, sfaces = self.ugrid_topology.device_arrays()
+            if target_ids is not None:
+                ids = target_ids.to(dev)
+                tree = CellTree2d(sxy, sfaces, -1, device=dev, clip_target_ids=(xy, faces, ids))
+            elif rows < other.size:
+                tree = CellTree2d(sxy, sfaces, -1, device=dev, clip_targets=(xy, faces, ranges[0][0], ranges[0][1]))
+            else:
+                tree = self.ugrid_topology.celltree
+        self.last_tree = tree
+        cap = max(self._ENTRIES_PER_ROW * rows, 65536)
+        indptr = torch.empty(rows + 1, dtype=torch.int64, device=dev)
+        indices = torch.empty(cap, dtype=torch.int32, device=dev)
+        data = torch.empty(cap, dtype=torch.float64, device=dev)
+        jobs = []
+        if target_ids is not None:
+            jobs.append(tree.intersect_faces_into(xy, faces, indptr, indices, data, relative=relative, ids=ids))
+        else:
+            first = ranges[0][0]
+            for c, (b, e) in enumerate(ranges):
+                if chunks is not None:
+                    tgt.wait_chunk(c)  # (the compute stream waits, not the host)
+                jobs.append(tree.intersect_faces_into(xy, faces, indptr[b - first: e - first + 1], indices, data,
+                                                      t_begin=b, t_end=e, relative=relative, chained=c > 0))
+        rebuild = lambda: self.overlap(other, relative, target_range, target_ids, deferred=False)
+        return sparse.PendingCSR(data, indices, indptr, rows, self.size, jobs, rebuild)
 
     def locate_centroids(self, other: "UnstructuredGrid2d", tolerance: Optional[float] = None,
                          target_range: Optional[Tuple[int, int]] = None):
@@ -361,6 +417,7 @@ class BaseRegridder(abc.ABC):
         self._source = setup_grid(source)
         self._target = setup_grid(target)
         self._weights = None
+        self._sharded_upload = bool(sharded_upload)
         if target_ids is not None:
             if target_range is not None:
                 raise ValueError("give target_range or target_ids, not both")
@@ -419,6 +476,24 @@ class BaseRegridder(abc.ABC):
     def _compute_weights(self, source, target, tolerance=None):
         pass
 
+    # The weights of the overlap regridders may still be in the making on the GPU when the
+    # constructor returns (sparse.PendingCSR): regrid() queues behind them; anything that
+    # needs the exact matrix on the host side (export, gather, nnz) settles them first.
+    @property
+    def _weights(self):
+        pending = self.__dict__.get("_pending")
+        if pending is not None:
+            self.__dict__["_settled"] = pending.finalize()
+            self.__dict__["_pending"] = None
+        return self.__dict__.get("_settled")
+
+    @_weights.setter
+    def _weights(self, value) -> None:
+        if isinstance(value, sparse.PendingCSR):
+            self.__dict__["_pending"], self.__dict__["_settled"] = value, None
+        else:
+            self.__dict__["_pending"], self.__dict__["_settled"] = None, value
+
     def _regrid(self, source: torch.Tensor, A, size: int) -> torch.Tensor:
         code, p = self._method
         return sparse.csr_apply(code, p, source, A, size)
@@ -431,9 +506,32 @@ class BaseRegridder(abc.ABC):
 
     def regrid_device(self, source: torch.Tensor) -> torch.Tensor:
         """(n_extra, source.size) float64 device tensor -> (n_extra, rows)."""
-        return self._regrid(source, self._weights, self._rows())
+        pending = self.__dict__.get("_pending")
+        A = pending.for_apply() if pending is not None else self._weights
+        return self._regrid(source, A, self._rows())
 
-    def _regrid_array(self, source):
+    def _upload_values(self, flat: torch.Tensor, dev) -> torch.Tensor:
+        """Pinned host values -> device on the COPY stream (behind whatever mesh upload is
+        still in flight there, next to the kernels that build the weights); 1/world per
+        rank + an all-gather over NVLink for a regridder built with sharded_upload."""
+        from .grid import _copy_stream
+
+        cs = _copy_stream(dev)
+        with torch.cuda.stream(cs):
+            if self._sharded_upload and flat.shape[0] == 1:
+                from .distributed import sharded_upload
+
+                src = sharded_upload(flat.reshape(-1), dev).reshape(1, -1)
+            else:
+                src = flat.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ev)
+        src.record_stream(cur)
+        return src
+
+    def _regrid_array(self, source, out=None):
         source_grid = self._source
         nd = source_grid.ndim
         if source.ndim < nd or tuple(source.shape[source.ndim - nd:]) != tuple(source_grid.shape):
@@ -443,37 +541,60 @@ class BaseRegridder(abc.ABC):
             )
         first_dims_shape = tuple(source.shape[: source.ndim - nd])
         is_tensor = isinstance(source, torch.Tensor)
-        dev = self._weights.data.device
+        pending = self.__dict__.get("_pending")
         host_tensor = is_tensor and not source.is_cuda
+        if pending is not None and not host_tensor:
+            # device data in: nothing below waits for the GPU, so settle the weights first
+            pending = None
+        dev = pending.data.device if pending is not None else self._weights.data.device
         if is_tensor:
-            src = source.reshape((-1, source_grid.size)).to(dev, non_blocking=True).to(torch.float64).contiguous()
+            flat = source.reshape((-1, source_grid.size))
+            if host_tensor and flat.is_pinned() and flat.dtype == torch.float64 and flat.is_contiguous():
+                src = self._upload_values(flat, dev)
+            else:
+                src = flat.to(dev, non_blocking=True).to(torch.float64).contiguous()
         else:
             a = np.ascontiguousarray(np.asarray(source).reshape((-1, source_grid.size)))
             src = torch.from_numpy(a).to(dev, non_blocking=True).to(torch.float64)
-        out = self.regrid_device(src)
+        res_d = self.regrid_device(src)
         if self._target_range is None:
             out_shape = first_dims_shape + tuple(self._target.shape)
         else:
             out_shape = first_dims_shape + (self._rows(),)
-        out = out.reshape(out_shape)
+        res_d = res_d.reshape(out_shape)
         if host_tensor:
             # host tensor in -> host tensor out (pinned if the input was): async D2H + one sync
-            res = torch.empty(out_shape, dtype=torch.float64, pin_memory=source.is_pinned())
-            res.copy_(out, non_blocking=True)
+            if out is not None:
+                if not isinstance(out, torch.Tensor) or out.is_cuda or tuple(out.shape) != tuple(out_shape) \
+                        or out.dtype != torch.float64:
+                    raise ValueError(f"out must be a float64 host tensor of shape {tuple(out_shape)}")
+                res = out
+            else:
+                res = torch.empty(out_shape, dtype=torch.float64, pin_memory=source.is_pinned())
+            res.copy_(res_d, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
+            if pending is not None and not pending.complete():
+                # the upper-bound arrays were too small: the weights are rebuilt (waiting
+                # path) and applied again
+                _ = self._weights
+                return self._regrid_array(source, out)
             return res
-        return out if is_tensor else out.cpu().numpy()
+        if out is not None:
+            raise ValueError("out= is for host tensors (the result of device data stays on the device)")
+        return res_d if is_tensor else res_d.cpu().numpy()
 
-    def regrid(self, data):
-        """regridder.py:212-262."""
+    def regrid(self, data, out=None):
+        """regridder.py:212-262.  ``out`` (host tensors only): a float64 host tensor of the
+        result's shape -- pinned, or a view of ``distributed.shared_host_array`` -- that
+        receives the result instead of a fresh allocation."""
         if isinstance(data, UgridDataArray):
-            out = self._regrid_array(data.data)
+            res = self._regrid_array(data.data, out)
             if isinstance(self._target, UnstructuredGrid2d) and self._target_range is None:
-                return UgridDataArray(out, self._target.ugrid_topology,
+                return UgridDataArray(res, self._target.ugrid_topology,
                                       data.dims[:-1] + (self._target.ugrid_topology.face_dimension,))
-            return out
+            return res
         elif isinstance(data, (np.ndarray, torch.Tensor)):
-            return self._regrid_array(data)
+            return self._regrid_array(data, out)
         raise TypeError(
             f"Expected UgridDataArray, numpy.ndarray or torch.Tensor, received: {type(data).__name__}"
         )
@@ -551,6 +672,7 @@ class BaseRegridder(abc.ABC):
         instance._source = setup_grid(_grid_from_dataset(weights, "__source"))
         instance._target_range = None
         instance._target_ids = None
+        instance._sharded_upload = False
         return instance
 
     @classmethod
@@ -616,7 +738,7 @@ class BaseOverlapRegridder(BaseRegridder, abc.ABC):
             return
         src, tgt = source.to_unstructured(), target.to_unstructured()
         self._weights = src.overlap(tgt, relative=relative, target_range=self._target_range,
-                                    target_ids=self._target_ids)
+                                    target_ids=self._target_ids, deferred=True)
 
 
 class OverlapRegridder(BaseOverlapRegridder):

@@ -105,6 +105,51 @@ class MatrixCSR(NamedTuple):
         )
 
 
+class PendingCSR:
+    """
+    CSR weights whose overlap jobs were enqueued WITHOUT waiting for them
+    (``CellTree2d.intersect_faces_into``): ``data`` / ``indices`` are sized by an upper
+    bound, the number of entries is only known on the device (``indptr[-1]``).  The apply
+    kernels need nothing else, so a regridder can queue ``regrid`` behind its own
+    construction while the host runs ahead.  ``finalize()`` waits, and returns the exact
+    ``MatrixCSR`` (views of the same arrays); if a job turned out incomplete -- candidate
+    arena or arrays too small -- the weights are rebuilt through the waiting path
+    (``rebuild``), which re-sizes.
+    """
+
+    def __init__(self, data, indices, indptr, n: int, m: int, jobs, rebuild):
+        self.data, self.indices, self.indptr = data, indices, indptr
+        self.n, self.m = int(n), int(m)
+        self._jobs, self._rebuild = list(jobs), rebuild
+        self._final = None
+        self._complete = None
+
+    def for_apply(self) -> "MatrixCSR":
+        """What csr_apply needs (row pointer + arrays); nnz is not known yet (-1)."""
+        return MatrixCSR(self.data, self.indices, self.indptr, self.n, self.m, -1)
+
+    def complete(self) -> bool:
+        """Waits for the jobs; False when one of them has to be redone."""
+        if self._complete is None:
+            ok, end = True, 0
+            for job in self._jobs:
+                _, end, good = job.result()
+                ok = ok and good
+            self._complete, self._nnz = ok, int(end)
+            self._jobs = []
+        return self._complete
+
+    def finalize(self) -> "MatrixCSR":
+        if self._final is None:
+            if self.complete():
+                nnz = self._nnz
+                self._final = MatrixCSR(self.data[:nnz], self.indices[:nnz], self.indptr, self.n, self.m, nnz)
+            else:
+                self._final = self._rebuild()
+            self.data = self.indices = self.indptr = None
+        return self._final
+
+
 def _check_index_range(index: torch.Tensor, size: int, name: str) -> None:
     """0 <= index < size (one min/max pass on the device)."""
     if index.numel() == 0:
