@@ -51,6 +51,7 @@ for nchunk in chunks:
         mark("start")
         r = xb.OverlapRegridder(src, tgt, method="mean")
         mark("weights done")
+        pend = r.__dict__.get("_pending")
         out = r.regrid(values)
         mark("regrid done (after D2H sync)")
         torch.cuda.synchronize()
@@ -61,3 +62,7 @@ for nchunk in chunks:
         rows += [(marks[0][1].elapsed_time(ev), f"[copy stream] {label} {name}") for name, ev in getattr(g, "_upload_events", [])]
     for t, name in sorted(rows):
         print(f"  {t:8.3f} ms  {name}")
+    if pend is not None:
+        pend.complete()
+        for j, ph in enumerate(pend.job_phase_ms):
+            print(f"  job {j}: " + "  ".join(f"{k} {v:.3f}" for k, v in ph.items()) + f"  sum {sum(ph.values()):.3f}")

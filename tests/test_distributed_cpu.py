@@ -141,3 +141,41 @@ def test_all_gather_csr_reassembles_sharded_weights():
         p.join(180)
         assert p.exitcode == 0
     assert all(q.get(timeout=10) is True for _ in range(world))
+
+
+def _shared_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from xugrid_b200.distributed import shared_host_array
+
+        n = 37
+        out = shared_host_array((2, n), torch.float64)
+        b, e = shard_range(n, rank, world)
+        # every rank writes only its own columns; after a barrier all of them read the whole array
+        out[:, b:e] = torch.arange(b, e, dtype=torch.float64)[None, :] + 100.0 * torch.arange(2, dtype=torch.float64)[:, None]
+        dist.barrier()
+        expect = torch.arange(n, dtype=torch.float64)[None, :] + 100.0 * torch.arange(2, dtype=torch.float64)[:, None]
+        second = shared_host_array(5, torch.int32)  # a second array gets its own segment
+        second[rank] = rank + 1
+        dist.barrier()
+        ok = bool(torch.equal(out, expect)) and second[:world].tolist() == list(range(1, world + 1))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_host_array_is_one_array_for_all_ranks():
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shared_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = dict(q.get(timeout=10) for _ in range(world))
+    assert got == {0: True, 1: True, 2: True}

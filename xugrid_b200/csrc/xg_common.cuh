@@ -141,7 +141,8 @@ void pinned_slot_release(double *p);
 // The packed, curve-ordered mesh + wide BVH.  Everything is in SORTED face
 // order except perm (sorted position -> caller's face id).
 struct xg_index {
-    int64_t n_face = 0, n_node = 0;
+    int64_t n_face = 0, n_node = 0;   // n_face: faces INDEXED (a culled index holds fewer than the mesh)
+    int64_t n_face_mesh = 0;          // faces of the mesh the index was built from
     int k = 0;
     int n_levels = 0;                 // number of node levels above the leaves
     int64_t level_n[xg::MAX_LEVELS];  // nodes per level (level 0 = groups of FANOUT leaves)

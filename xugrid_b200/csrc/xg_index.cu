@@ -574,7 +574,7 @@ static int index_create_impl(const double *d_xy, int64_t n_node, const void *d_f
     cudaStream_t s = (cudaStream_t)stream;
     ensure_pool_config();
     xg_index *ix = new xg_index();
-    ix->n_face = n_face; ix->n_node = n_node; ix->k = k;
+    ix->n_face = n_face; ix->n_face_mesh = n_face; ix->n_node = n_node; ix->k = k;
     const bool culled = h_clip_box || targets;
 
     // level sizes

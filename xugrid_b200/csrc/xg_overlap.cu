@@ -1129,7 +1129,8 @@ static int enqueue_move_rows(xg_overlap *job, const int64_t *d_indptr, int32_t *
 
 // buffers every attempt needs + the packed targets; returns the default arena capacity
 static int overlap_prepare(xg_overlap *job, const double *d_t_xy, const void *d_t_faces, int idx_bytes,
-                           const int32_t *d_t_ids, int64_t t_begin, int64_t t_end, unsigned long long *cap_out) {
+                           const int32_t *d_t_ids, int64_t n_t_mesh, int64_t t_begin, int64_t t_end,
+                           unsigned long long *cap_out) {
     const xg_index *source = job->src;
     cudaStream_t s = job->s;
     const int64_t n_t = job->n_t;
@@ -1163,7 +1164,13 @@ static int overlap_prepare(xg_overlap *job, const double *d_t_xy, const void *d_
 
     unsigned long long cap = (unsigned long long)n_t * PAIRS_PER_TARGET_GUESS;
     if (cap < 65536) cap = 65536;
-    if (source->n_face > 2 * n_t && n_t >= 32 * SAMPLE_STRIDE * 8) {
+    // "source much finer than the targets" compares meshes over the same area: an index
+    // culled to these targets against the targets, a whole-mesh index against the whole
+    // target mesh -- not against the few rows of one range of it (a regridder that consumes
+    // its target mesh range by range while it is uploaded runs many such jobs, and the
+    // sampling pass costs a host round trip each)
+    const int64_t n_t_area = (source->n_face < source->n_face_mesh || d_t_ids) ? n_t : (n_t_mesh > n_t ? n_t_mesh : n_t);
+    if (source->n_face > 2 * n_t_area && n_t >= 32 * SAMPLE_STRIDE * 8) {
         unsigned long long est = 0;
         rc = estimate_candidates(job, &est);  // (one host round trip)
         if (rc) return rc;
@@ -1213,7 +1220,7 @@ static int overlap_begin_impl(const xg_index *source, const double *d_t_xy, int6
             return XG_OK;
         }
         unsigned long long cap = 0;
-        rc = overlap_prepare(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, t_begin, t_end, &cap);
+        rc = overlap_prepare(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, n_t_face, t_begin, t_end, &cap);
         if (rc) goto fail;
         unsigned long long needed = 0;
         rc = overlap_attempt(job, cap, d_indptr, &needed);
@@ -1306,7 +1313,7 @@ extern "C" int xg_overlap_run(const xg_index *source, const double *d_t_xy, int6
         return XG_OK;
     }
     unsigned long long cap = 0;
-    rc = overlap_prepare(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, t_begin, t_end, &cap);
+    rc = overlap_prepare(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, n_t_face, t_begin, t_end, &cap);
     if (rc) return fail(rc);
     rc = overlap_enqueue(job, cap, d_indptr, chained != 0);
     if (rc) return fail(rc);

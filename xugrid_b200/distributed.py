@@ -137,6 +137,40 @@ def sharded_upload(host: torch.Tensor, device: torch.device,
     return recv[:n]
 
 
+def bind_to_gpu_cpus(device_index: int):
+    """
+    Restrict this process to the CPU cores that NVML reports as local to its GPU (same
+    NUMA node / PCIe root complex), BEFORE it allocates pinned host memory: Linux places
+    pages on the node of the core that first touches them, and a rank whose staging
+    buffers sit on the other socket pulls every host<->device copy over the inter-socket
+    link.  One process per GPU makes this a per-process setting.  Returns the set of cores,
+    or None when nothing was changed (no NVML, no affinity information, or an empty
+    intersection with the cores the process may use).
+    """
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cores = local & allowed
+        if not cores or cores == allowed:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None
+
+
 _shared_arrays = []  # (tensor, path): registered host mappings are kept alive for the process
 
 
@@ -171,9 +205,10 @@ def shared_host_array(shape, dtype: torch.dtype = torch.float64,
     dist.barrier(group)
     if rank == 0:
         os.unlink(path)  # the mappings stay; the name does not outlive the job
-    err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), numel * t.element_size(), 0)
-    if int(err) != 0:
-        raise RuntimeError(f"cudaHostRegister of the shared host array failed: {err}")
+    if torch.cuda.is_available():  # (the gloo tests of the host logic map it without a GPU)
+        err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), numel * t.element_size(), 0)
+        if int(err) != 0:
+            raise RuntimeError(f"cudaHostRegister of the shared host array failed: {err}")
     _shared_arrays.append((t, path))
     return t[: math.prod(shape)].reshape(shape) if math.prod(shape) else t[:0].reshape(shape)
 

@@ -118,9 +118,10 @@ class UnstructuredGrid2d:
         if deferred:
             rows = (other.size if target_range is None else target_range[1] - target_range[0]) \
                 if target_ids is None else int(target_ids.numel())
-            # (a source much finer than the targets needs a sampled arena size: waiting path)
-            if rows > 0 and self.size <= 2 * rows:
-                return self._overlap_deferred(other, relative, target_range, target_ids, rows)
+            if rows > 0:
+                pending = self._overlap_deferred(other, relative, target_range, target_ids, rows)
+                if pending is not None:
+                    return pending
         if target_ids is not None:
             # a share of the targets given by face numbers: index only the source faces
             # they can touch, rows in the order of the list
@@ -129,7 +130,9 @@ class UnstructuredGrid2d:
             xy, faces = other.ugrid_topology.device_arrays()
             sxy, sfaces = self.ugrid_topology.device_arrays()
             ids = target_ids.to(xy.device)
-            tree = CellTree2d(sxy, sfaces, -1, device=sxy.device, clip_target_ids=(xy, faces, ids))
+            tree = self.__dict__.pop("_tree_for_waiting_path", None)  # (built by the deferred attempt)
+            if tree is None:
+                tree = CellTree2d(sxy, sfaces, -1, device=sxy.device, clip_target_ids=(xy, faces, ids))
             self.last_tree = tree
             indptr, indices, data = tree.intersect_faces_csr(xy, faces, -1, relative=relative, ids=ids)
             return MatrixCSR(data, indices, indptr, int(ids.numel()), self.size, int(data.numel()))
@@ -160,7 +163,9 @@ class UnstructuredGrid2d:
 
             sxy, sfaces = self.ugrid_topology.device_arrays()
             # (the clip box = bounds of the target range is reduced on the device)
-            tree = CellTree2d(sxy, sfaces, -1, device=sxy.device, clip_targets=(xy, faces, t_begin, t_end))
+            tree = self.__dict__.pop("_tree_for_waiting_path", None)  # (built by the deferred attempt)
+            if tree is None:
+                tree = CellTree2d(sxy, sfaces, -1, device=sxy.device, clip_targets=(xy, faces, t_begin, t_end))
         elif tree is None:
             tree = self.ugrid_topology.celltree
         self.last_tree = tree
@@ -195,6 +200,15 @@ class UnstructuredGrid2d:
             else:
                 tree = self.ugrid_topology.celltree
         self.last_tree = tree
+        # (source faces indexed for these targets; known on the host: a culled build waits for it)
+        n_src = tree.n_indexed if tree.n_face > 2 * rows else tree.n_face
+        n_ref = rows if (n_src < tree.n_face or target_ids is not None) else max(rows, other.size)
+        if n_src > 2 * n_ref:
+            # a source much finer than the targets: its rows outgrow any fixed bound, and the
+            # library samples the candidate density first (waiting path)
+            if tree is not self.ugrid_topology._celltree:
+                self._tree_for_waiting_path = tree  # (a culled index: the waiting path takes it over)
+            return None
         cap = max(self._ENTRIES_PER_ROW * rows, 65536)
         indptr = torch.empty(rows + 1, dtype=torch.int64, device=dev)
         indices = torch.empty(cap, dtype=torch.int32, device=dev)

@@ -132,9 +132,11 @@ class PendingCSR:
         """Waits for the jobs; False when one of them has to be redone."""
         if self._complete is None:
             ok, end = True, 0
+            self.job_phase_ms = []  # device time per phase of every job (profiling)
             for job in self._jobs:
                 _, end, good = job.result()
                 ok = ok and good
+                self.job_phase_ms.append(job.phase_ms)
             self._complete, self._nnz = ok, int(end)
             self._jobs = []
         return self._complete
