@@ -213,6 +213,47 @@ int xg_locate_points(const xg_index *index, const double *d_points, int64_t n_po
 int xg_barycentric(const xg_index *index, const double *d_points, int64_t n_point,
                    double tolerance, int32_t *d_face_index, double *d_weights, void *stream);
 
+/* ---- Voronoi preparation of the barycentric interpolator -------------------
+ * Replaces voronoi_topology(add_exterior=True, add_vertices=True, skip_concave=True)
+ * (xugrid/ugrid/voronoi.py:330-458) as called from UnstructuredGrid2d.barycentric
+ * (xugrid/regrid/unstructured.py:146-175): the polygons around the NODES of a mesh whose
+ * vertices are the centroids of the adjacent faces (d_centroids, (n_face, 2), e.g. from
+ * xg_face_centroid); around an exterior node also the projections of the boundary faces'
+ * centroids on the two exterior edges that meet there and one corner vertex (the node
+ * itself, or the midpoint of the two projections at a concave corner).
+ * xg_voronoi_begin analyses the mesh and returns sizes[0] = interior polygons,
+ * sizes[1] = exterior polygons (= exterior nodes), sizes[2] = projection vertices kept,
+ * sizes[3] = largest polygon (the stream is synchronised).  The caller allocates
+ *   d_vertices    (n_face + sizes[2] + sizes[1], 2) float64: [centroids | projections | corners]
+ *   d_polygons    (sizes[0] + sizes[1], sizes[3]) int32, -1 fill, counter-clockwise;
+ *                 interior polygons first, each group in ascending node number
+ *   d_vertex_face (n_vertex) int32: the face whose value a vertex carries, -1 for corners
+ *   d_corner_map  (sizes[1], 2) int32: the two projection vertices a corner sits between
+ * and xg_voronoi_finish fills them and releases the job (xg_voronoi_abort: release only).
+ * The caller's mesh arrays must stay alive between the two calls. */
+typedef struct xg_voronoi xg_voronoi;
+int xg_voronoi_begin(const double *d_xy, int64_t n_node, const void *d_faces, int idx_bytes,
+                     int64_t n_face, int k, const double *d_centroids, int64_t sizes[4],
+                     void *stream, xg_voronoi **job);
+int xg_voronoi_finish(xg_voronoi *job, double *d_vertices, int32_t *d_polygons, int32_t *d_vertex_face,
+                      int32_t *d_corner_map, void *stream);
+int xg_voronoi_abort(xg_voronoi *job);
+/* The assembly behind xg_barycentric over the Voronoi polygons
+ * (xugrid/regrid/unstructured.py:176-201 with replace_interpolated_weights, :17-57):
+ * d_weights (n_point, kv) is adjusted IN PLACE -- the weight of a corner vertex goes to its
+ * two projection vertices, inversely proportional to distance; points whose d_source_face
+ * (xg_locate_points on the SOURCE mesh) is -1 get zero weights -- the positive weights per
+ * point are counted, d_indptr (n_point + 1) is written and nnz returned (the stream is
+ * synchronised).  xg_bary_csr_fill then writes the CSR entries: column = the source face of
+ * the polygon vertex, in the polygon's vertex order. */
+int xg_bary_csr_count(const int32_t *d_poly_index, double *d_weights, int64_t n_point, int kv,
+                      const int32_t *d_polygons, const int32_t *d_vertex_face,
+                      const int32_t *d_corner_map, const double *d_vertices, int64_t corner_start,
+                      const int32_t *d_source_face, int64_t *d_indptr, int64_t *h_nnz, void *stream);
+int xg_bary_csr_fill(const int32_t *d_poly_index, const double *d_weights, int64_t n_point, int kv,
+                     const int32_t *d_polygons, const int32_t *d_vertex_face, const int64_t *d_indptr,
+                     int32_t *d_indices, double *d_data, void *stream);
+
 /* ---- per-face geometry ----------------------------------------------------
  * connectivity.area (xugrid/ugrid/connectivity.py:615-633) and
  * connectivity.centroids (connectivity.py:636-664). */

@@ -23,21 +23,12 @@ def run():
         ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append((name, ev))
     mark("start")
     cen = grid.centroids_device; mark("centroids")
-    topo = voronoi.voronoi_topology(faces, xy, cen); mark("voronoi_topology")
+    topo = voronoi.voronoi_topology_device(faces, xy, cen); mark("voronoi_topology (kernels)")
     vor_tree = CellTree2d(topo.vertices, topo.faces, -1, device=dev); mark("voronoi index")
-    face_index, weights = vor_tree.compute_barycentric_weights_device(points, None); mark("barycentric kernel")
-    conn = topo.faces[face_index.long().clamp(min=0)]; mark("conn gather")
-    voronoi.redistribute_corner_weights(topo, conn, weights); mark("corner weights")
+    polygon_index, weights = vor_tree.compute_barycentric_weights_device(points, None); mark("barycentric kernel")
     tree = CellTree2d(xy, faces, -1, device=dev); mark("source index")
-    outside = tree.locate_points_device(points) == -1; mark("locate (outside mask)")
-    weights[outside] = 0
-    keep = weights > 0
-    source_index = topo.vertex_face[conn.clamp(min=0)]
-    counts = keep.sum(dim=1)
-    indptr = torch.zeros(points.shape[0] + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(counts, 0, out=indptr[1:])
-    indices = source_index[keep].to(torch.int32)
-    data = weights[keep]; mark("CSR assembly")
+    source_face = tree.locate_points_device(points); mark("locate (outside mask)")
+    indptr, indices, data = voronoi.weights_to_csr_device(topo, polygon_index, weights, source_face); mark("CSR assembly (kernels)")
     torch.cuda.synchronize()
     return marks, topo
 

@@ -58,6 +58,11 @@ SIGNATURES = {
     "xg_overlap_stats": (_int, [_vp, ctypes.POINTER(_i64)]),
     "xg_overlap_timings": (_int, [_vp, ctypes.POINTER(_dbl)]),
     "xg_overlap_abort": (_int, [_vp]),
+    "xg_voronoi_begin": (_int, [_vp, _i64, _vp, _int, _i64, _int, _vp, ctypes.POINTER(_i64), _vp, ctypes.POINTER(_vp)]),
+    "xg_voronoi_finish": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "xg_voronoi_abort": (_int, [_vp]),
+    "xg_bary_csr_count": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, ctypes.POINTER(_i64), _vp]),
+    "xg_bary_csr_fill": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "xg_locate_points": (_int, [_vp, _vp, _i64, _dbl, _vp, _vp]),
     "xg_barycentric": (_int, [_vp, _vp, _i64, _dbl, _vp, _vp, _vp]),
     "xg_intersect_edges": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, ctypes.POINTER(_i64), _vp]),

@@ -20,7 +20,7 @@ BUILD = os.path.join(HERE, "_build")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libxgregrid.so")
 
-SOURCES = ["xg_index.cu", "xg_overlap.cu", "xg_locate.cu", "xg_apply.cu"]
+SOURCES = ["xg_index.cu", "xg_overlap.cu", "xg_locate.cu", "xg_apply.cu", "xg_voronoi.cu"]
 
 # -fmad=false: fp64 products and sums round separately, like the reference's
 # numba/LLVM code on x86, so areas and weighted sums are reproducible bit for bit.

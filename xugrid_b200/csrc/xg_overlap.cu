@@ -832,12 +832,14 @@ struct ClipArgs {
 template <int KT, int KS, int BT, int MINB>
 static int launch_clip(const ClipArgs &A, cudaStream_t s) {
     int per_sm = 1;
-    const size_t smem_sat = sizeof(double2) * 2 * (size_t)(KT + KS) * BT;  // two staged pairs per thread
-    XG_CUDA(cudaFuncSetAttribute(k_sat<KT, KS, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sat));
-    XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sat<KT, KS, BT>, BT, smem_sat));
+    // (the filter keeps its own block size: it is tuned separately from the clip kernel)
+    constexpr int SBT = (KT + KS <= 8) ? 256 : BT;
+    const size_t smem_sat = sizeof(double2) * 2 * (size_t)(KT + KS) * SBT;  // two staged pairs per thread
+    XG_CUDA(cudaFuncSetAttribute(k_sat<KT, KS, SBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sat));
+    XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sat<KT, KS, SBT>, SBT, smem_sat));
     if (per_sm < 1) per_sm = 1;
-    k_sat<KT, KS, BT><<<NUM_SMS * per_sm, BT, smem_sat, s>>>(A.pairs, A.cap, (const double2 *)A.tpoly, A.tnv, A.kt,
-                                                     (const double2 *)A.spoly, A.snv, A.ks, A.surv, A.ctr);
+    k_sat<KT, KS, SBT><<<NUM_SMS * per_sm, SBT, smem_sat, s>>>(A.pairs, A.cap, (const double2 *)A.tpoly, A.tnv, A.kt,
+                                                       (const double2 *)A.spoly, A.snv, A.ks, A.surv, A.ctr);
     XG_CHECK_LAUNCH();
     if (A.between) XG_CUDA(cudaEventRecord(A.between, s));
     size_t smem = sizeof(double2) * 3 * (size_t)(KT + KS) * BT;  // 2 ping-pong lists + 1 staged pair

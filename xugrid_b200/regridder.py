@@ -263,20 +263,13 @@ class UnstructuredGrid2d:
             # a shard: the rows of its own target faces (the Voronoi mesh of the source is
             # replicated, like the source mesh of the overlap regridders)
             points = points[target_range[0]:target_range[1]].contiguous()
-        topo = voronoi.voronoi_topology(faces, xy, grid.centroids_device)
+        # Voronoi polygons by the library's kernels (csrc/xg_voronoi.cu), barycentric weights
+        # inside them, then corner weights / outside mask / CSR rows in two more kernels
+        topo = voronoi.voronoi_topology_device(faces, xy, grid.centroids_device)
         vor_tree = CellTree2d(topo.vertices, topo.faces, -1, device=xy.device)
-        face_index, weights = vor_tree.compute_barycentric_weights_device(points, tolerance)
-        conn = topo.faces[face_index.long().clamp(min=0)]
-        voronoi.redistribute_corner_weights(topo, conn, weights)
-        outside = grid.celltree.locate_points_device(points) == -1
-        weights[outside] = 0
-        keep = weights > 0
-        source_index = topo.vertex_face[conn.clamp(min=0)]
-        counts = keep.sum(dim=1)
-        indptr = torch.zeros(points.shape[0] + 1, dtype=torch.int64, device=xy.device)
-        torch.cumsum(counts, 0, out=indptr[1:])
-        indices = source_index[keep].to(torch.int32)
-        data = weights[keep]
+        polygon_index, weights = vor_tree.compute_barycentric_weights_device(points, tolerance)
+        source_face = grid.celltree.locate_points_device(points)
+        indptr, indices, data = voronoi.weights_to_csr_device(topo, polygon_index, weights, source_face)
         return MatrixCSR(data, indices, indptr, int(points.shape[0]), self.size, int(data.numel()))
 
     def intersection_length(self, other: "Network1d", relative: bool):

@@ -205,6 +205,72 @@ def voronoi_topology(faces: torch.Tensor, xy: torch.Tensor, centroids: torch.Ten
     return VoronoiTopology(vertices, vor_faces, vertex_face, corner_map, corner_start)
 
 
+def voronoi_topology_device(faces: torch.Tensor, xy: torch.Tensor, centroids: torch.Tensor) -> VoronoiTopology:
+    """The same topology built by the library's kernels (csrc/xg_voronoi.cu; CUDA tensors
+    in, int32 index tensors out): what ``UnstructuredGrid2d.barycentric`` runs.  The
+    tensor-op version above stays as the statement the kernels are tested against."""
+    import ctypes
+
+    from . import _native
+
+    L = _native.lib()
+    dev = xy.device
+    F, k = int(faces.shape[0]), int(faces.shape[1])
+    sizes = (ctypes.c_int64 * 4)()
+    job = ctypes.c_void_p()
+    with torch.cuda.device(dev):
+        s = _native.stream_ptr()
+        _native.check(L.xg_voronoi_begin(_native.ptr(xy, torch.float64), int(xy.shape[0]), _native.ptr(faces),
+                                         faces.element_size(), F, k, _native.ptr(centroids, torch.float64), sizes, s,
+                                         ctypes.byref(job)))
+        try:
+            n_int, n_ext, n_keep, kmax = (int(v) for v in sizes)
+            n_vertex = F + n_keep + n_ext
+            vertices = torch.empty((n_vertex, 2), dtype=torch.float64, device=dev)
+            polygons = torch.empty((n_int + n_ext, kmax), dtype=torch.int32, device=dev)
+            vertex_face = torch.empty(n_vertex, dtype=torch.int32, device=dev)
+            corner_map = torch.empty((n_ext, 2), dtype=torch.int32, device=dev)
+        except BaseException:
+            L.xg_voronoi_abort(job)
+            raise
+        _native.check(L.xg_voronoi_finish(job, _native.ptr(vertices), _native.ptr(polygons), _native.ptr(vertex_face),
+                                          _native.ptr(corner_map), s))
+    return VoronoiTopology(vertices, polygons, vertex_face, corner_map, F + n_keep)
+
+
+def weights_to_csr_device(topo: VoronoiTopology, polygon_index: torch.Tensor, weights: torch.Tensor,
+                          source_face: torch.Tensor):
+    """unstructured.py:176-201 on the device (``xg_bary_csr_count`` / ``_fill``): corner
+    weights redistributed (``weights`` is adjusted in place), points outside the source
+    mesh (``source_face == -1``) dropped, positive weights as CSR rows.  Returns
+    (indptr int64, indices int32, data float64)."""
+    import ctypes
+
+    from . import _native
+
+    L = _native.lib()
+    dev = weights.device
+    n, kv = int(weights.shape[0]), int(weights.shape[1])
+    if kv != int(topo.faces.shape[1]):
+        raise ValueError("weights and Voronoi polygons disagree on the number of vertices per polygon")
+    indptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    nnz = ctypes.c_int64()
+    with torch.cuda.device(dev):
+        s = _native.stream_ptr()
+        _native.check(L.xg_bary_csr_count(
+            _native.ptr(polygon_index, torch.int32), _native.ptr(weights, torch.float64), n, kv,
+            _native.ptr(topo.faces, torch.int32), _native.ptr(topo.vertex_face, torch.int32),
+            _native.ptr(topo.corner_map, torch.int32), _native.ptr(topo.vertices, torch.float64),
+            int(topo.corner_start), _native.ptr(source_face, torch.int32), _native.ptr(indptr), ctypes.byref(nnz), s))
+        indices = torch.empty(nnz.value, dtype=torch.int32, device=dev)
+        data = torch.empty(nnz.value, dtype=torch.float64, device=dev)
+        _native.check(L.xg_bary_csr_fill(
+            _native.ptr(polygon_index, torch.int32), _native.ptr(weights, torch.float64), n, kv,
+            _native.ptr(topo.faces, torch.int32), _native.ptr(topo.vertex_face, torch.int32), _native.ptr(indptr),
+            _native.ptr(indices), _native.ptr(data), s))
+    return indptr, indices, data
+
+
 def redistribute_corner_weights(topo: VoronoiTopology, conn: torch.Tensor, weights: torch.Tensor) -> None:
     """
     In place.  ``conn`` (n_point, k) are the vertices of the polygon every point
