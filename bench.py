@@ -320,8 +320,13 @@ def run_ours(args) -> int:
             area = torch.empty(cap, dtype=torch.float64, device=dev)
             state["job"] = tree.intersect_faces_into(src["txy"], src["tf"], indptr, indices, area, t_begin=tb, t_end=te)
             A = sparse.MatrixCSR(area, indices, indptr, rows, n_s, -1)
-        local = sparse.csr_apply(0, 0.0, src["values"], A, rows)
-        full = all_gather_columns(local, n_t) if (world > 1 and gather) else local
+        if world > 1 and gather and state.get("peer_out") is not None:
+            # apply fused with the all-gather: the kernel stores this rank's columns into the
+            # output copy of every rank over NVLink (symmetric memory), no collective
+            full = state["peer_out"].apply(0, 0.0, src["values"], A)
+        else:
+            local = sparse.csr_apply(0, 0.0, src["values"], A, rows)
+            full = all_gather_columns(local, n_t) if (world > 1 and gather) else local
         state["tree"], state["A"], state["apply_in"], state["rows"] = tree, A, src["values"], rows
         return full
 
@@ -395,6 +400,15 @@ def run_ours(args) -> int:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    state["peer_out"] = None
+    if world > 1 and not by_curve and not os.environ.get("XG_BENCH_NCCL_GATHER"):
+        try:
+            from xugrid_b200.distributed import GatheredOutput
+
+            state["peer_out"] = GatheredOutput(1, n_t, device=dev)
+        except Exception as exc:  # no peer access between these GPUs: NCCL all-gather instead
+            print(f"rank {rank}: symmetric memory unavailable ({exc}); using the NCCL all-gather", file=sys.stderr)
+            state["peer_out"] = None
     sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("XG_BENCH_NO_SMI")) else None
     ms_dev = timed(lambda: step(d), args.steps, args.warmup)
     if state.get("job") is not None:
@@ -469,7 +483,10 @@ def run_ours(args) -> int:
                        "sharding": (f"{rows} targets of rank 0's patch along the space-filling curve ({world} ranks)"
                                     if by_curve else f"target rows [{b},{e}) on rank 0 of {world}"),
                        "source_faces_indexed_on_rank0": n_indexed, "cub_launches_per_step": 12,
-                       "rank0_bound_to_gpu_local_cores": len(numa_cores) if numa_cores else None},
+                       "rank0_bound_to_gpu_local_cores": len(numa_cores) if numa_cores else None,
+                       "output_assembly": (None if world == 1 else
+                                           "apply kernel stores into every rank's copy over NVLink (xg_csr_apply_peers, symmetric memory)"
+                                           if state.get("peer_out") is not None else "NCCL all_gather_into_tensor")},
             "e2e": {"value": n_t / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "note": "the grids stage their arrays ONCE per grid in pinned host memory, connectivity "

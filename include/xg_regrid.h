@@ -288,6 +288,17 @@ int xg_intersect_edges(const xg_index *index, const double *d_edges, int64_t n_e
 int xg_csr_apply(int method, double percentile, const int64_t *d_indptr, const int32_t *d_indices,
                  const double *d_weights, const double *d_src, int64_t n_extra, int64_t m,
                  int64_t n_rows, double *d_out, int64_t out_ld, void *stream);
+/* The apply FUSED with the all-gather that reassembles the output of a job whose target
+ * rows are sharded over the GPUs of one box (the reference has no counterpart):
+ * h_d_outs is a HOST array of n_out (<= 16) DEVICE pointers, one per rank of the job, each
+ * the position of this rank's first column in that rank's copy of the (n_extra, n_target)
+ * output (peer memory mapped over NVLink, e.g. torch symmetric memory); every result is
+ * stored to all of them from inside the kernel, so the transfer overlaps the reduction and
+ * no send slab, pad or collective launch is needed.  The caller orders the ranks around the
+ * call (a device-side barrier before peers may be overwritten and after the kernel). */
+int xg_csr_apply_peers(int method, double percentile, const int64_t *d_indptr, const int32_t *d_indices,
+                       const double *d_weights, const double *d_src, int64_t n_extra, int64_t m,
+                       int64_t n_rows, double *const *h_d_outs, int n_out, int64_t out_ld, void *stream);
 /* Replaces CentroidLocatorRegridder._regrid (xugrid/regrid/regridder.py:400-409):
  *   out[e, row[q]] = src[e, col[q]], NaN elsewhere.  d_out is (n_extra, size). */
 int xg_coo_gather(const int32_t *d_row, const int32_t *d_col, int64_t nnz, const double *d_src,

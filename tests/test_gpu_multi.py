@@ -57,6 +57,18 @@ def _worker(rank, world, port, order, q):
             r.gather_weights()
             again = r.regrid(torch.from_numpy(values).cuda())
             ok = ok and bool(torch.equal(again.contiguous().view(torch.int64), full.view(torch.int64)))
+        # the apply fused with the all-gather (peer stores into every rank's copy of the output)
+        # against apply + NCCL all-gather, twice (the second call overwrites what peers have read)
+        from xugrid_b200.distributed import GatheredOutput
+
+        gathered = GatheredOutput(3, n_t)
+        dv = torch.from_numpy(values).cuda()
+        for method in ("mean", "maximum"):
+            r = xb.OverlapRegridder(source, target, method=method, target_range=(b, e))
+            expect = all_gather_columns(r.regrid(dv), n_t).contiguous()
+            code, p = r._method
+            got = gathered.apply(code, p, dv, r._weights)
+            ok = ok and bool(torch.equal(got.view(torch.int64), expect.view(torch.int64)))
         # shares along the space-filling curve (compact whatever the face numbering) + scatter by ids
         dxy, dtf = target.device_arrays()
         ids = curve_shard(dxy, dtf, rank, world)

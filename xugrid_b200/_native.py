@@ -69,6 +69,7 @@ SIGNATURES = {
     "xg_face_area": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp]),
     "xg_face_centroid": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp]),
     "xg_csr_apply": (_int, [_int, _dbl, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "xg_csr_apply_peers": (_int, [_int, _dbl, _vp, _vp, _vp, _vp, _i64, _i64, _i64, ctypes.POINTER(_vp), _int, _i64, _vp]),
     "xg_coo_gather": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp]),
 }
 

@@ -182,11 +182,26 @@ __device__ __forceinline__ double r_conservative(const Row &r) {
     return w_sum == 0 ? NAN : v_agg;
 }
 
+// Where a result goes: one array, or the same position of the output array of EVERY rank of
+// the job (peer device memory mapped over NVLink / NVSwitch).  The second form is the apply
+// fused with the all-gather that reassembles the output: a rank's rows are stored straight
+// into all copies while the kernel runs, instead of into a send slab that a collective
+// then moves (xg_csr_apply_peers).
+constexpr int MAX_PEERS = 16;
+struct OutSet {
+    double *p[MAX_PEERS];
+    int n;
+    __device__ __forceinline__ void store(int64_t at, double v) const {
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) p[i][at] = v;
+    }
+};
+
 template <int METHOD>
 __global__ void __launch_bounds__(256)
 k_csr_apply(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
             const double *__restrict__ weights, const double *__restrict__ src, int64_t n_extra,
-            int64_t m, int64_t n_rows, double percentile, double *__restrict__ out, int64_t out_ld) {
+            int64_t m, int64_t n_rows, double percentile, const OutSet out, int64_t out_ld) {
     const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (row >= n_rows) return;
     const int64_t a = indptr[row], b = indptr[row + 1];
@@ -209,7 +224,7 @@ k_csr_apply(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indi
             else if (METHOD == XG_MAX_OVERLAP) res = r_max_overlap(r);
             else if (METHOD == XG_CONSERVATIVE) res = r_conservative(r);
         }
-        out[e * out_ld + row] = res;
+        out.store(e * out_ld + row, res);
     }
 }
 
@@ -248,7 +263,7 @@ template <int METHOD>
 __global__ void __launch_bounds__(256)
 k_csr_apply_steps(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                   const double *__restrict__ weights, const double *__restrict__ src, int64_t n_extra,
-                  int64_t m, int64_t n_rows, double *__restrict__ out, int64_t out_ld) {
+                  int64_t m, int64_t n_rows, const OutSet out, int64_t out_ld) {
     const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (row >= n_rows) return;
     const int64_t a = indptr[row], b = indptr[row + 1];
@@ -269,7 +284,7 @@ k_csr_apply_steps(const int64_t *__restrict__ indptr, const int32_t *__restrict_
         }
 #pragma unroll
         for (int u = 0; u < APPLY_E; ++u)
-            if (u < ne) out[(e0 + u) * out_ld + row] = (b > a) ? acc[u].result() : NAN;
+            if (u < ne) out.store((e0 + u) * out_ld + row, (b > a) ? acc[u].result() : NAN);
     }
 }
 
@@ -349,13 +364,13 @@ k_face_centroid(const double2 *__restrict__ xy, const I *__restrict__ faces, int
 
 using namespace xg;
 
-extern "C" int xg_csr_apply(int method, double percentile, const int64_t *d_indptr,
-                            const int32_t *d_indices, const double *d_weights, const double *d_src,
-                            int64_t n_extra, int64_t m, int64_t n_rows, double *d_out,
-                            int64_t out_ld, void *stream) {
+static int csr_apply_impl(int method, double percentile, const int64_t *d_indptr,
+                          const int32_t *d_indices, const double *d_weights, const double *d_src,
+                          int64_t n_extra, int64_t m, int64_t n_rows, const OutSet d_out,
+                          int64_t out_ld, void *stream) {
     if (n_rows < 0 || n_extra < 0 || m < 0 || out_ld < n_rows) { set_error("xg_csr_apply: invalid size"); return XG_ERR_INVALID; }
     if (n_rows == 0 || n_extra == 0) return XG_OK;
-    if (!d_indptr || !d_out) { set_error("xg_csr_apply: NULL argument"); return XG_ERR_INVALID; }
+    if (!d_indptr) { set_error("xg_csr_apply: NULL argument"); return XG_ERR_INVALID; }
     if (method == XG_PERCENTILE && !(percentile >= 0.0 && percentile <= 100.0)) {
         set_error("percentile must be in the range [0, 100], received: %g", percentile);
         return XG_ERR_INVALID;
@@ -449,4 +464,32 @@ extern "C" int xg_face_centroid(const double *d_xy, const void *d_faces, int idx
     else k_face_centroid<int64_t><<<G, 256, 0, s>>>((const double2 *)d_xy, (const int64_t *)d_faces, n_face, k, (double2 *)d_centroid_xy);
     XG_CHECK_LAUNCH();
     return XG_OK;
+}
+
+extern "C" int xg_csr_apply(int method, double percentile, const int64_t *d_indptr,
+                            const int32_t *d_indices, const double *d_weights, const double *d_src,
+                            int64_t n_extra, int64_t m, int64_t n_rows, double *d_out,
+                            int64_t out_ld, void *stream) {
+    if (!d_out && n_rows > 0 && n_extra > 0) { set_error("xg_csr_apply: NULL argument"); return XG_ERR_INVALID; }
+    OutSet O;
+    O.n = 1;
+    O.p[0] = d_out;
+    return csr_apply_impl(method, percentile, d_indptr, d_indices, d_weights, d_src, n_extra, m, n_rows, O, out_ld, stream);
+}
+
+extern "C" int xg_csr_apply_peers(int method, double percentile, const int64_t *d_indptr,
+                                  const int32_t *d_indices, const double *d_weights, const double *d_src,
+                                  int64_t n_extra, int64_t m, int64_t n_rows, double *const *h_d_outs,
+                                  int n_out, int64_t out_ld, void *stream) {
+    if (!h_d_outs || n_out < 1 || n_out > MAX_PEERS) {
+        set_error("xg_csr_apply_peers: between 1 and %d output arrays", MAX_PEERS);
+        return XG_ERR_INVALID;
+    }
+    OutSet O;
+    O.n = n_out;
+    for (int i = 0; i < n_out; ++i) {
+        if (!h_d_outs[i] && n_rows > 0 && n_extra > 0) { set_error("xg_csr_apply_peers: NULL output"); return XG_ERR_INVALID; }
+        O.p[i] = h_d_outs[i];
+    }
+    return csr_apply_impl(method, percentile, d_indptr, d_indices, d_weights, d_src, n_extra, m, n_rows, O, out_ld, stream);
 }

@@ -203,19 +203,48 @@ __global__ void k_frame_from_red(const unsigned long long *red, double *frame) {
 // [xmin, xmax, ymin, ymax], e.g. the bounds of a rank's target range reduced on the
 // device a moment ago) are kept, appended compactly and counted
 
+// position of every node relative to the clip box of a culled build: bit 0 = at or left of
+// xmin, 1 = at or right of xmax, 2 = at or below ymin, 3 = at or above ymax.  The bbox of a
+// face misses the box (strictly) exactly when all its nodes share one of the four bits, so
+// the pass over ALL faces of the replicated source mesh that every rank makes reads the
+// connectivity and k bytes per face; coordinates are gathered for the kept faces only.
+__global__ void __launch_bounds__(256)
+k_node_outcodes(const double2 *__restrict__ xy, int64_t n_node, const double *__restrict__ clip,
+                uint8_t *__restrict__ code) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_node) return;
+    const double2 p = xy[i];
+    code[i] = (uint8_t)((p.x <= clip[0] ? 1 : 0) | (p.x >= clip[1] ? 2 : 0) | (p.y <= clip[2] ? 4 : 0) |
+                        (p.y >= clip[3] ? 8 : 0));
+}
+
 template <typename I, int KMAX>
 __global__ void __launch_bounds__(256)
 k_face_keys(const double2 *__restrict__ xy, const I *__restrict__ faces, int64_t f_begin,
             int64_t n, int k, const double *__restrict__ frame, uint32_t *__restrict__ keys,
             int32_t *__restrict__ ids, unsigned long long *diag2_max, const double *__restrict__ clip,
-            unsigned long long *__restrict__ kept, const int32_t *__restrict__ face_ids) {
+            unsigned long long *__restrict__ kept, const int32_t *__restrict__ face_ids,
+            const uint8_t *__restrict__ outcode) {
     // face_ids (optional): the faces to key are face_ids[f_begin + i]; what is recorded in
     // `ids` is then the position in that list, not the face number
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     double d2 = 0.0;
     bool in_box = false;
     uint32_t my_key = 0;
-    if (i < n) {
+    bool culled_by_nodes = false;
+    if (i < n && outcode) {
+        const I *face = faces + (face_ids ? (int64_t)face_ids[f_begin + i] : f_begin + i) * k;
+        unsigned all = 0xfu;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+            if (j >= k) break;
+            const I idx = face[j];
+            if (idx < 0) break;
+            all &= outcode[idx];
+        }
+        culled_by_nodes = all != 0u;
+    }
+    if (i < n && !culled_by_nodes) {
         const I *face = faces + (face_ids ? (int64_t)face_ids[f_begin + i] : f_begin + i) * k;
         double2 p = xy[face[0]];
         double xmin = p.x, xmax = p.x, ymin = p.y, ymax = p.y;
@@ -412,13 +441,13 @@ template <typename I>
 static int launch_face_keys(const double2 *xy, const I *faces, int64_t f_begin, int64_t n, int k,
                             const double *frame, uint32_t *keys, int32_t *ids,
                             unsigned long long *diag2, const double *clip, unsigned long long *kept,
-                            const int32_t *face_ids, cudaStream_t s) {
+                            const int32_t *face_ids, cudaStream_t s, const uint8_t *outcode = nullptr) {
     if (n == 0) return XG_OK;
     const int B = 256;
     const unsigned G = (unsigned)div_up(n, B);
-    if (k <= 3) k_face_keys<I, 3><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept, face_ids);
-    else if (k <= 4) k_face_keys<I, 4><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept, face_ids);
-    else k_face_keys<I, XG_MAX_N_VERTEX><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept, face_ids);
+    if (k <= 3) k_face_keys<I, 3><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept, face_ids, outcode);
+    else if (k <= 4) k_face_keys<I, 4><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept, face_ids, outcode);
+    else k_face_keys<I, XG_MAX_N_VERTEX><<<G, B, 0, s>>>(xy, faces, f_begin, n, k, frame, keys, ids, diag2, clip, kept, face_ids, outcode);
     XG_CHECK_LAUNCH();
     return XG_OK;
 }
@@ -458,7 +487,7 @@ static void ensure_pool_config() {
 int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
               int64_t f_end, int k, const double *d_frame, unsigned long long *d_diag2,
               PackedMesh *out, cudaStream_t s, const double *d_clip_box, unsigned long long *d_kept,
-              const int32_t *d_face_ids) {
+              const int32_t *d_face_ids, int64_t n_node) {
     ensure_pool_config();
     const int64_t n = f_end - f_begin;
     out->n = n;
@@ -466,7 +495,12 @@ int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_
     const double *clip = (d_clip_box && d_kept) ? d_clip_box : nullptr;
     if (clip) XG_CUDA(cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), s));
     const double2 *xy = reinterpret_cast<const double2 *>(d_xy);
-    DevBuf keys_in, keys_out, ids_in, tmp;
+    DevBuf keys_in, keys_out, ids_in, tmp, outcode;
+    if (clip && n_node > 0) {
+        XG_CUDA(outcode.alloc((size_t)n_node, s));
+        k_node_outcodes<<<(unsigned)div_up(n_node, 256), 256, 0, s>>>(xy, n_node, clip, outcode.as<uint8_t>());
+        XG_CHECK_LAUNCH();
+    }
     XG_CUDA(keys_in.alloc(sizeof(uint32_t) * (size_t)n, s));
     XG_CUDA(keys_out.alloc(sizeof(uint32_t) * (size_t)n, s));
     XG_CUDA(ids_in.alloc(sizeof(int32_t) * (size_t)n, s));
@@ -474,11 +508,11 @@ int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_
     if (idx_bytes == 4)
         rc = launch_face_keys<int32_t>(xy, (const int32_t *)d_faces, f_begin, n, k, d_frame,
                                        keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, clip, d_kept,
-                                       d_face_ids, s);
+                                       d_face_ids, s, outcode.as<uint8_t>());
     else
         rc = launch_face_keys<int64_t>(xy, (const int64_t *)d_faces, f_begin, n, k, d_frame,
                                        keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, clip, d_kept,
-                                       d_face_ids, s);
+                                       d_face_ids, s, outcode.as<uint8_t>());
     if (rc) return rc;
     int64_t n_pack = n;
     if (clip) {
@@ -640,7 +674,7 @@ static int index_create_impl(const double *d_xy, int64_t n_node, const void *d_f
         PackedMesh pm;
         pm.perm = ix->perm; pm.box = ix->leaf_box; pm.poly = ix->poly; pm.nvert = ix->nvert;
         rc = pack_mesh(d_xy, d_faces, idx_bytes, 0, n_face, k, d_frame, d_red + 4, &pm, s,
-                       culled ? d_clip : nullptr, d_red + 5, nullptr);
+                       culled ? d_clip : nullptr, d_red + 5, nullptr, culled ? n_node : 0);
         if (rc) break;
         if (culled) {
             // only the faces that can meet the box are indexed

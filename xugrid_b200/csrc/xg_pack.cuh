@@ -26,6 +26,7 @@ struct PackedMesh {
 int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
               int64_t f_end, int k, const double *d_frame, unsigned long long *d_diag2,
               PackedMesh *out, cudaStream_t s, const double *d_clip_box = nullptr,
-              unsigned long long *d_kept = nullptr, const int32_t *d_face_ids = nullptr);
+              unsigned long long *d_kept = nullptr, const int32_t *d_face_ids = nullptr,
+              int64_t n_node = 0);  // n_node > 0 with a clip box: cull by node outcodes first
 
 }  // namespace xg

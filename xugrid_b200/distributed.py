@@ -65,6 +65,53 @@ def all_gather_columns(local: torch.Tensor, n_total: int, group: Optional[dist.P
     return full
 
 
+class GatheredOutput:
+    """
+    The (n_extra, n_total) output of a job whose target columns are sharded by
+    ``shard_range`` over the ranks, assembled WITHOUT a collective: the buffer lives in
+    symmetric memory (every rank maps every rank's copy over NVLink / NVSwitch) and the
+    apply kernel of rank r stores its columns into all copies while it computes them
+    (``xg_csr_apply_peers``).  Replaces ``csr_apply`` + ``all_gather_columns`` (send slab,
+    padding, NCCL launch): at 8 ranks and 10 M columns 0.04 + 0.20 ms become one kernel.
+
+    ``apply(code, percentile, source, A)`` runs the fused kernel between two device-side
+    barriers of the group -- peers must be done reading the previous result before it is
+    overwritten, and all stores must have landed before anybody reads -- and returns this
+    rank's full (n_extra, n_total) copy.  Outside a process group it is a plain apply.
+    """
+
+    def __init__(self, n_extra: int, n_total: int, device=None, group: Optional[dist.ProcessGroup] = None):
+        self.n_extra, self.n_total = int(n_extra), int(n_total)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.world == 1:
+            self.buf = torch.empty((self.n_extra, self.n_total), dtype=torch.float64, device=dev)
+            self.handle, self.peer_ptrs = None, [self.buf.data_ptr()]
+            return
+        import torch.distributed._symmetric_memory as symm
+
+        self.buf = symm.empty((self.n_extra, self.n_total), dtype=torch.float64, device=dev)
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(self.peer_ptrs) != self.world or len(self.peer_ptrs) > 16:
+            raise RuntimeError("symmetric memory rendezvous returned an unexpected number of peers")
+
+    def apply(self, code: int, percentile: float, source: torch.Tensor, A) -> torch.Tensor:
+        from . import sparse
+
+        b, e = shard_range(self.n_total, self.rank, self.world)
+        if A.n != e - b:
+            raise ValueError(f"rank {self.rank} holds {A.n} rows, expected {e - b}")
+        if self.handle is not None:
+            self.handle.barrier(channel=0)
+        sparse.csr_apply_peers(code, percentile, source, A, self.peer_ptrs, self.n_total, b)
+        if self.handle is not None:
+            self.handle.barrier(channel=1)
+        return self.buf
+
+
 def all_gather_csr(local, n_total: int, group: Optional[dist.ProcessGroup] = None):
     """
     ``local`` is this rank's MatrixCSR over the target rows

@@ -240,6 +240,31 @@ def csr_apply(
     return out
 
 
+def csr_apply_peers(code: int, percentile: float, source: torch.Tensor, A: MatrixCSR, out_ptrs, out_ld: int,
+                    column_begin: int) -> None:
+    """``csr_apply`` whose results go to SEVERAL (n_extra, out_ld) arrays at once -- the copies
+    of the output on all ranks of a sharded job, given as raw device pointers of peer-mapped
+    memory (``distributed.GatheredOutput``): row r of ``A`` lands in column
+    ``column_begin + r`` of every array (``xg_csr_apply_peers``)."""
+    import ctypes
+
+    L = _native.lib()
+    _check_source(source, A, "csr_apply_peers")
+    n_extra, m = int(source.shape[0]), int(source.shape[1])
+    rows = int(A.indptr.numel()) - 1
+    if column_begin < 0 or column_begin + rows > out_ld:
+        raise ValueError("the rows do not fit the output arrays")
+    ptrs = (ctypes.c_void_p * len(out_ptrs))(*[int(p) + 8 * int(column_begin) for p in out_ptrs])
+    with torch.cuda.device(source.device):
+        _native.check(
+            L.xg_csr_apply_peers(
+                code, float(percentile), _native.ptr(A.indptr, torch.int64), _native.ptr(A.indices, torch.int32),
+                _native.ptr(A.data, torch.float64), _native.ptr(source.contiguous(), torch.float64), n_extra, m,
+                rows, ptrs, len(out_ptrs), int(out_ld), _native.stream_ptr(),
+            )
+        )
+
+
 def coo_gather(source: torch.Tensor, A: MatrixCOO, size: int) -> torch.Tensor:
     """``CentroidLocatorRegridder._regrid`` (regridder.py:400-409) on the device."""
     L = _native.lib()
