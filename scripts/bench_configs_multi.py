@@ -205,7 +205,8 @@ if 5 in which:
     local, cons_ms = timed(lambda: sparse.csr_apply(9, 0.0, vals, R, R.n))
     cons = xd.all_gather_by_ids(local, all_ids, lens, n_t)
     if rank == 0:
-        o_ptr, o_idx, o_w = oracle_rows(sxy, sf, txy, tf, sample, relative=True)
+        # (relative weights = the absolute ones over the area of their source face: no second tree)
+        o_w = o_w / oracle.face_area(sxy, sf)[o_idx]
         o_out = oracle.csr_apply("first_order_conservative", vals.cpu().numpy(), o_w, o_idx, o_ptr, len(sample))
         got = cons[:, torch.from_numpy(sample).to(dev)].cpu().numpy()
         check["first_order_conservative_close_1e-12"] = bool(np.allclose(got, o_out, rtol=1e-12, atol=0, equal_nan=True))

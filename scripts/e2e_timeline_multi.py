@@ -24,9 +24,12 @@ n_side = int(sys.argv[1]) if len(sys.argv) > 1 else 2236
 sxy, sf = synthetic.jittered_lattice(n_side, n_side, 10, "tri")
 txy, tf = synthetic.jittered_lattice(n_side + 3, n_side - 2, 11, "tri")
 n_t = tf.shape[0]
-values = torch.from_numpy(np.random.default_rng(12).random((1, sf.shape[0]))).pin_memory()
 if world > 1:
+    bound = None if os.environ.get("XG_BENCH_NO_BIND") else xd.bind_to_gpu_cpus(local_rank)
     dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        print("rank 0 bound to", None if bound is None else len(bound), "cores local to its GPU")
+values = torch.from_numpy(np.random.default_rng(12).random((1, sf.shape[0]))).pin_memory()
 h_out = xd.shared_host_array((1, n_t), torch.float64)
 src = xb.Ugrid2d(sxy[:, 0], sxy[:, 1], -1, sf, device=dev)
 tgt = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf, device=dev)
