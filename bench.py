@@ -499,7 +499,11 @@ def run_ours(args) -> int:
                             "once); that one-off host work is outside the timed region and h2d_bytes counts the "
                             "int32 bytes that really cross PCIe every step",
                     "one_off_staging_ms": staging_ms},
-            "gpu_launches": 6 + n_levels + 9 + 1,
+            # this repo's own kernels per resident step: index (bounds 3, keys, pack, tolerance, one per
+            # BVH level; a culled build 4 more: target-range bounds 3 + node outcodes), overlap job
+            # (keys, pack, walk, filter, clip, counts, capacity check, three row movers, void-rows),
+            # apply; plus 14 CUB launches (2 radix sorts of 5, 2 scans of 2)
+            "gpu_launches": (6 + n_levels + (4 if world > 1 else 0)) + 11 + 1,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved"], "peak": peak,
                          "unit": "GB/s", "frac": dk["frac"], "traffic": dk["traffic"],
                          "frac_measured_dram": dk["frac_measured_dram"],

@@ -13,6 +13,7 @@ import time
 import numpy as np
 import torch
 
+import oracle
 import xugrid_b200 as xb
 from xugrid_b200 import sparse, synthetic
 
@@ -50,6 +51,69 @@ def emit(d):
     print(json.dumps(d), flush=True)
 
 
+N_SAMPLE = 2_000 if small else 20_000
+
+
+def overlap_rows_equal_oracle(sxy, sf, txy, tf, A, seed):
+    """pair set and weights of N_SAMPLE target rows of a device CSR against the CPU oracle"""
+    import os
+
+    oracle.set_num_threads(os.cpu_count() or 1)
+    sample = np.sort(np.random.default_rng(seed).choice(len(tf), min(N_SAMPLE, len(tf)), replace=False))
+    ti, si, w = oracle.CellTree2d(sxy, sf).intersect_faces(txy, np.ascontiguousarray(tf[sample]))
+    order = np.lexsort((si, ti))
+    ti, si, w = ti[order], si[order], w[order]
+    o_ptr = oracle.coo_to_csr(ti, len(sample))
+    ip = A.indptr.cpu().numpy()
+    lo, hi = ip[sample], ip[sample + 1]
+    same_counts = bool(np.array_equal(hi - lo, np.diff(o_ptr)))
+    take = torch.from_numpy(np.concatenate([np.arange(a, b) for a, b in zip(lo, hi)])).to(A.data.device)
+    idx = A.indices[take].cpu().numpy().astype(np.int64)
+    wd = A.data[take].cpu().numpy()
+    return {"sample_targets": int(len(sample)), "pair_set_equal": same_counts and bool(np.array_equal(idx, si)),
+            "weights_bit_identical": same_counts and bool(np.array_equal(wd.view(np.int64), w.view(np.int64)))}
+
+
+def bary_rows_close_to_oracle(sxy, sf, mid, A, reg):
+    """BarycentricInterpolator rows of N_SAMPLE raster points against the CPU statement of the same
+    path: Voronoi topology by the tensor-op version on CPU tensors (pinned by the reference's golden
+    vectors), point location / Wachspress weights by the oracle, corner redistribution and outside
+    mask as in unstructured.py:146-201.  Columns exact, weights to 1e-10."""
+    from xugrid_b200 import voronoi
+
+    nr = len(mid)
+    sample = np.sort(np.random.default_rng(22).choice(nr * nr, min(N_SAMPLE, nr * nr), replace=False))
+    # the very points the regridder queried: the centroids of the raster cells as laid out on the
+    # device (they differ from the midpoints in the last bit, which a Wachspress weight next to a
+    # polygon edge magnifies to 1e-12)
+    from xugrid_b200.regridder import _target_points
+
+    pts = _target_points(reg._target, dev)[torch.from_numpy(sample).to(dev)].cpu().numpy()
+    assert np.allclose(pts, np.column_stack([mid[sample % nr], mid[sample // nr]]), rtol=0, atol=1e-12)  # C order: row = y index
+    cent = oracle.face_centroids(sxy, sf)
+    topo = voronoi.voronoi_topology(torch.from_numpy(sf), torch.from_numpy(sxy), torch.from_numpy(cent))
+    tree = oracle.CellTree2d(topo.vertices.numpy(), topo.faces.numpy(), -1)
+    fi, w = tree.compute_barycentric_weights(pts)
+    conn = topo.faces[torch.from_numpy(fi).clamp(min=0)]
+    w = torch.from_numpy(w)
+    voronoi.redistribute_corner_weights(topo, conn, w)
+    outside = oracle.CellTree2d(sxy, sf, -1).locate_points(pts) == -1
+    w[torch.from_numpy(outside)] = 0
+    keep = w > 0
+    o_cnt = keep.sum(1).numpy()
+    o_idx = topo.vertex_face[conn.clamp(min=0)][keep].numpy()
+    o_w = w[keep].numpy()
+    ip = A.indptr.cpu().numpy()
+    lo, hi = ip[sample], ip[sample + 1]
+    same_counts = bool(np.array_equal(hi - lo, o_cnt))
+    take = torch.from_numpy(np.concatenate([np.arange(a, b) for a, b in zip(lo, hi)])).to(A.data.device)
+    idx = A.indices[take].cpu().numpy().astype(np.int64)
+    wd = A.data[take].cpu().numpy()
+    return {"sample_points": int(len(sample)), "columns_equal": same_counts and bool(np.array_equal(idx, o_idx)),
+            "weights_close_1e-10": same_counts and bool(np.allclose(wd, o_w, rtol=1e-10, atol=1e-15)),
+            "max_abs_weight_diff": float(np.abs(wd - o_w).max()) if same_counts and len(o_w) else None}
+
+
 if 2 in which:
     n = 50_000 if small else 500_000
     t0 = time.time()
@@ -74,6 +138,7 @@ if 2 in which:
           "checks": {"rows_fully_covered_frac": float(inside.double().mean()),
                      "row_sum_never_exceeds_area": bool((row_sum <= t_area * (1 + 1e-9)).all()),
                      "mean_of_constant_max_rel_err": float(((ones[~torch.isnan(ones)] - 3.5).abs() / 3.5).max())},
+          "oracle_check": overlap_rows_equal_oracle(sxy, sf, txy, tf, A, 13),
           "host_mesh_generation_s": gen_s})
     del tree, A, vals, out
 
@@ -105,7 +170,8 @@ if 3 in which:
           "build_ms": build_ms, "apply_ms": apply_ms, "points_per_s_build": nr * nr / (build_ms * 1e-3), "nnz": A.nnz,
           "checks": {"rows_with_weights_frac": float(has.double().mean()),
                      "max_abs_row_sum_minus_1": float((row_sum[has] - 1.0).abs().max()),
-                     "linear_field_max_abs_err": float((got[ok] - want[ok]).abs().max())}})
+                     "linear_field_max_abs_err": float((got[ok] - want[ok]).abs().max())},
+          "oracle_check": bary_rows_close_to_oracle(sxy, sf, mid, A, reg)})
     del reg, A, vals, out, source, target
 
 if 4 in which:

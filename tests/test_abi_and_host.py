@@ -164,3 +164,38 @@ def test_ugrid1d_and_network1d_host_logic():
         xb.Ugrid1d(node_xy[:, 0], node_xy[:, 1], -1, np.array([[0, 1, 2]]))
     with pytest.raises(ValueError):
         xb.UgridDataArray(np.zeros(3), net)
+
+
+def test_pending_csr_settles_or_rebuilds():
+    """sparse.PendingCSR (weights whose overlap jobs were enqueued without waiting): exact views
+    once the jobs report complete, the rebuild closure when one of them does not"""
+    import torch
+
+    from xugrid_b200 import sparse
+
+    class Job:
+        def __init__(self, nnz, end, ok):
+            self._r, self.phase_ms, self.calls = (nnz, end, ok), {"pack": 0.0}, 0
+
+        def result(self):
+            self.calls += 1
+            return self._r
+
+    data = torch.arange(10, dtype=torch.float64)
+    indices = torch.arange(10, dtype=torch.int32)
+    indptr = torch.tensor([0, 2, 5, 7], dtype=torch.int64)
+    jobs = [Job(5, 5, True), Job(2, 7, True)]
+    rebuilt = []
+    p = sparse.PendingCSR(data, indices, indptr, 3, 9, jobs, lambda: rebuilt.append(1))
+    A = p.for_apply()
+    assert A.nnz == -1 and A.n == 3 and A.m == 9 and A.data is data
+    assert p.complete() and p.complete()
+    assert [j.calls for j in jobs] == [1, 1]  # asked once
+    W = p.finalize()
+    assert W.nnz == 7 and W.data.numel() == 7 and W.indices.numel() == 7 and W.indptr is indptr and not rebuilt
+    assert p.finalize() is W and len(p.job_phase_ms) == 2
+    # one incomplete job: the waiting path is asked for the weights instead
+    marker = sparse.MatrixCSR(data[:1], indices[:1], indptr[:2], 1, 9, 1)
+    q = sparse.PendingCSR(data, indices, indptr, 3, 9, [Job(5, 5, True), Job(0, 5, False)], lambda: marker)
+    assert not q.complete()
+    assert q.finalize() is marker

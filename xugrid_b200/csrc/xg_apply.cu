@@ -431,7 +431,7 @@ extern "C" int xg_coo_gather(const int32_t *d_row, const int32_t *d_col, int64_t
     if (nnz < 0 || n_extra < 0 || size < 0 || m < 0) { set_error("xg_coo_gather: invalid size"); return XG_ERR_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
     if (n_extra * size > 0) {
-        k_fill_nan<<<NUM_SMS * 8, 256, 0, s>>>(d_out, n_extra * size);
+        k_fill_nan<<<num_sms() * 8, 256, 0, s>>>(d_out, n_extra * size);
         XG_CHECK_LAUNCH();
     }
     if (nnz > 0 && n_extra > 0) {

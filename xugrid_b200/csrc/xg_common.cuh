@@ -20,7 +20,9 @@ namespace xg {
 constexpr int WARP = 32;
 constexpr int FANOUT = 32;          // children per node of the packed wide BVH
 constexpr int MAX_LEVELS = 8;       // 32^8 faces is far beyond HBM capacity
-constexpr int NUM_SMS = 148;        // B200
+// SMs of the current device (148 on a B200), asked once per device: persistent kernels launch
+// one or a few blocks per SM
+int num_sms();
 
 // leaf / node bounding box, celltree layout [xmin, xmax, ymin, ymax]
 struct __align__(32) Box {

@@ -40,6 +40,20 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     return XG_ERR_CUDA;
 }
 
+int num_sms() {
+    static std::mutex mu;
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
 // ---- block cache (see xg_common.cuh) ----------------------------------------------
 struct CachedBlock {
     void *p;
@@ -576,10 +590,10 @@ static int launch_range_bounds(const TargetRange &t, unsigned long long *d_red, 
     const int64_t n = t.end - t.begin;
     if (n <= 0) return XG_OK;
     if (t.idx_bytes == 4)
-        k_face_range_bounds<int32_t><<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)t.d_xy, (const int32_t *)t.d_faces,
+        k_face_range_bounds<int32_t><<<num_sms() * 4, 256, 0, s>>>((const double2 *)t.d_xy, (const int32_t *)t.d_faces,
                                                                t.begin, n, t.k, d_red, t.d_ids);
     else
-        k_face_range_bounds<int64_t><<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)t.d_xy, (const int64_t *)t.d_faces,
+        k_face_range_bounds<int64_t><<<num_sms() * 4, 256, 0, s>>>((const double2 *)t.d_xy, (const int64_t *)t.d_faces,
                                                                t.begin, n, t.k, d_red, t.d_ids);
     XG_CHECK_LAUNCH();
     return XG_OK;
@@ -658,7 +672,7 @@ static int index_create_impl(const double *d_xy, int64_t n_node, const void *d_f
     do {
         k_init_red<<<1, 1, 0, s>>>(d_red);
         if (n_node > 0)
-            k_node_bounds<<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)d_xy, n_node, d_red);
+            k_node_bounds<<<num_sms() * 4, 256, 0, s>>>((const double2 *)d_xy, n_node, d_red);
         k_frame_from_red<<<1, 1, 0, s>>>(d_red, d_frame);
         if (cudaGetLastError() != cudaSuccess) { rc = XG_ERR_CUDA; set_error("index: launch failed"); break; }
         if (h_clip_box) {
@@ -862,7 +876,7 @@ extern "C" int xg_target_shard(const double *d_xy, int64_t n_node, const void *d
     XG_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned int) * SHARD_BINS, s));
     XG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), s));
     k_init_red<<<1, 1, 0, s>>>(d_red);
-    if (n_node > 0) k_node_bounds<<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)d_xy, n_node, d_red);
+    if (n_node > 0) k_node_bounds<<<num_sms() * 4, 256, 0, s>>>((const double2 *)d_xy, n_node, d_red);
     k_frame_from_red<<<1, 1, 0, s>>>(d_red, d_frame);
     XG_CHECK_LAUNCH();
     int rc;
@@ -906,10 +920,10 @@ extern "C" int xg_face_range_bounds(const double *d_xy, const void *d_faces, int
     const int64_t n = f_end - f_begin;
     if (n > 0) {
         if (idx_bytes == 4)
-            k_face_range_bounds<int32_t><<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)d_xy, (const int32_t *)d_faces,
+            k_face_range_bounds<int32_t><<<num_sms() * 4, 256, 0, s>>>((const double2 *)d_xy, (const int32_t *)d_faces,
                                                                    f_begin, n, k, red.as<unsigned long long>(), nullptr);
         else
-            k_face_range_bounds<int64_t><<<NUM_SMS * 4, 256, 0, s>>>((const double2 *)d_xy, (const int64_t *)d_faces,
+            k_face_range_bounds<int64_t><<<num_sms() * 4, 256, 0, s>>>((const double2 *)d_xy, (const int64_t *)d_faces,
                                                                    f_begin, n, k, red.as<unsigned long long>(), nullptr);
     }
     k_frame_from_red<<<1, 1, 0, s>>>(red.as<unsigned long long>(), frame.as<double>());

@@ -838,7 +838,7 @@ static int launch_clip(const ClipArgs &A, cudaStream_t s) {
     XG_CUDA(cudaFuncSetAttribute(k_sat<KT, KS, SBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sat));
     XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sat<KT, KS, SBT>, SBT, smem_sat));
     if (per_sm < 1) per_sm = 1;
-    k_sat<KT, KS, SBT><<<NUM_SMS * per_sm, SBT, smem_sat, s>>>(A.pairs, A.cap, (const double2 *)A.tpoly, A.tnv, A.kt,
+    k_sat<KT, KS, SBT><<<num_sms() * per_sm, SBT, smem_sat, s>>>(A.pairs, A.cap, (const double2 *)A.tpoly, A.tnv, A.kt,
                                                        (const double2 *)A.spoly, A.snv, A.ks, A.surv, A.ctr);
     XG_CHECK_LAUNCH();
     if (A.between) XG_CUDA(cudaEventRecord(A.between, s));
@@ -847,7 +847,7 @@ static int launch_clip(const ClipArgs &A, cudaStream_t s) {
     XG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem));
     if (per_sm < 1) per_sm = 1;
-    kern<<<NUM_SMS * per_sm, BT, smem, s>>>(A.surv, A.ctr, (const double2 *)A.tpoly, A.tnv, A.kt,
+    kern<<<num_sms() * per_sm, BT, smem, s>>>(A.surv, A.ctr, (const double2 *)A.tpoly, A.tnv, A.kt,
                                             (const double2 *)A.spoly, A.snv, A.ks, A.prov_ptr, A.fill_cnt, A.prov_col,
                                             A.prov_val);
     XG_CHECK_LAUNCH();
@@ -920,7 +920,7 @@ static TraverseParams traverse_params(const xg_index *source) {
 // blocks of the persistent walk over `tiles` tiles of 32 targets
 static unsigned traverse_grid(int64_t tiles) {
     const int64_t groups = div_up(tiles, TRAV_WARPS);
-    const int64_t resident = (int64_t)NUM_SMS * TRAV_BLOCKS_PER_SM;
+    const int64_t resident = (int64_t)num_sms() * TRAV_BLOCKS_PER_SM;
     return (unsigned)(groups < resident ? (groups > 0 ? groups : 1) : resident);
 }
 
@@ -970,7 +970,7 @@ static int overlap_enqueue(xg_overlap *job, unsigned long long cap, int64_t *d_i
                                 cudaMemcpyDeviceToDevice, s));
     XG_CUDA(job->pairs.alloc(sizeof(int2) * (size_t)cap, s));
     // (+ the unused tails of the last survivor windows: at most 8 blocks of 8 warps per SM)
-    XG_CUDA(job->surv.alloc(sizeof(int2) * ((size_t)cap + (size_t)NUM_SMS * 64 * SAT_WIN), s));
+    XG_CUDA(job->surv.alloc(sizeof(int2) * ((size_t)cap + (size_t)num_sms() * 64 * SAT_WIN), s));
     XG_CUDA(job->prov_col.alloc(sizeof(int32_t) * (size_t)cap, s));
     // cnt = [cand_cnt | fill_cnt | row_cnt], (n_t + 1) int32 each
     XG_CUDA(cudaMemsetAsync(job->cnt.p, 0, sizeof(int32_t) * 2 * (size_t)(n_t + 1), s));
@@ -1118,8 +1118,8 @@ static int enqueue_move_rows(xg_overlap *job, const int64_t *d_indptr, int32_t *
     k_move_rows<<<(unsigned)div_up(job->n_t, 256), 256, 0, s>>>(R, job->n_t, long_rows, n_long);
     unsigned long long *n_huge = job->ctr.as<unsigned long long>() + CTR_HUGE;
     int32_t *huge_rows = long_rows + job->n_t;  // second n_t ints of the same 32 * n_t byte buffer
-    k_move_long_rows<<<NUM_SMS * 4, 128, 0, s>>>(R, long_rows, n_long, huge_rows, n_huge);
-    k_move_huge_rows<<<NUM_SMS, 1024, 0, s>>>(R, huge_rows, n_huge);
+    k_move_long_rows<<<num_sms() * 4, 128, 0, s>>>(R, long_rows, n_long, huge_rows, n_huge);
+    k_move_huge_rows<<<num_sms(), 1024, 0, s>>>(R, huge_rows, n_huge);
     XG_CHECK_LAUNCH();
     if (entry_cap != INT64_MAX) {
         k_void_rows<<<(unsigned)div_up(job->n_t, 256), 256, 0, s>>>(const_cast<int64_t *>(d_indptr), job->n_t,
