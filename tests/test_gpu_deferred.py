@@ -155,3 +155,37 @@ def test_regridder_falls_back_when_the_bound_is_too_small(xb, monkeypatch):
     assert not pending.complete()
     assert torch.equal(out.view(torch.int64), good.view(torch.int64))
     assert r._weights.nnz > len(tf)
+
+
+@pytest.mark.parametrize("bound", [16, 1])
+def test_ranges_are_applied_and_downloaded_as_they_finish(xb, monkeypatch, bound):
+    """a target mesh uploaded in face ranges: chained jobs, apply + D2H per range on the side
+    stream (regridder._drain_ranges); bound=1: the arrays are too small and everything is redone"""
+    from xugrid_b200 import regridder
+
+    sxy, sf = synthetic.jittered_lattice(250, 240, 41, "mixed")
+    txy, tf = synthetic.jittered_lattice(260, 250, 42, "tri")
+    values = torch.from_numpy(np.random.default_rng(9).random((3, len(sf)))).pin_memory()
+    values[1, ::7] = float("nan")
+    src = xb.Ugrid2d(sxy[:, 0], sxy[:, 1], -1, sf)
+    whole = xb.OverlapRegridder(src, xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf), method="mean")
+    assert len(whole.__dict__["_pending"].ranges) == 1
+    good = whole.regrid(values)
+    monkeypatch.setattr(regridder.BaseRegridder, "_CHUNK_MIN_FACES", 1000)
+    monkeypatch.setattr(regridder.BaseRegridder, "_TARGET_CHUNKS", (0.1, 0.45, 0.8, 1.0))
+    monkeypatch.setattr(regridder.UnstructuredGrid2d, "_ENTRIES_PER_ROW", bound)
+    for cls, method in ((xb.OverlapRegridder, "mean"), (xb.RelativeOverlapRegridder, "first_order_conservative")):
+        tgt = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf)  # fresh: nothing resident, the upload is chunked
+        r = cls(src, tgt, method=method)
+        pending = r.__dict__["_pending"]
+        assert len(pending.ranges) == 4 and pending.ranges[-1][1] == len(tf)
+        out = r.regrid(values)
+        assert pending.complete() == (bound == 16)
+        if cls is xb.OverlapRegridder:
+            assert torch.equal(out.view(torch.int64), good.view(torch.int64))
+        else:
+            expect = cls(src, xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf), method=method).regrid(values.cuda()).cpu()
+            assert torch.equal(out.view(torch.int64), expect.view(torch.int64))
+        # and once more on the settled weights (the ordinary path)
+        again = r.regrid(values)
+        assert torch.equal(again.view(torch.int64), out.view(torch.int64))

@@ -213,7 +213,7 @@ class UnstructuredGrid2d:
         indptr = torch.empty(rows + 1, dtype=torch.int64, device=dev)
         indices = torch.empty(cap, dtype=torch.int32, device=dev)
         data = torch.empty(cap, dtype=torch.float64, device=dev)
-        jobs = []
+        jobs, range_events = [], []
         if target_ids is not None:
             jobs.append(tree.intersect_faces_into(xy, faces, indptr, indices, data, relative=relative, ids=ids))
         else:
@@ -223,8 +223,13 @@ class UnstructuredGrid2d:
                     tgt.wait_chunk(c)  # (the compute stream waits, not the host)
                 jobs.append(tree.intersect_faces_into(xy, faces, indptr[b - first: e - first + 1], indices, data,
                                                       t_begin=b, t_end=e, relative=relative, chained=c > 0))
+                done = torch.cuda.Event()
+                done.record()
+                range_events.append((b - first, e - first, done))
         rebuild = lambda: self.overlap(other, relative, target_range, target_ids, deferred=False)
-        return sparse.PendingCSR(data, indices, indptr, rows, self.size, jobs, rebuild)
+        pending = sparse.PendingCSR(data, indices, indptr, rows, self.size, jobs, rebuild)
+        pending.ranges = range_events
+        return pending
 
     def locate_centroids(self, other: "UnstructuredGrid2d", tolerance: Optional[float] = None,
                          target_range: Optional[Tuple[int, int]] = None):
@@ -358,6 +363,17 @@ class _StructuredAdapter:
         }
 
 
+_drain_streams = {}
+
+
+def _drain_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """High-priority side stream for apply + download of finished target ranges."""
+    key = (dev.type, dev.index)
+    if key not in _drain_streams:
+        _drain_streams[key] = torch.cuda.Stream(device=dev, priority=-1)
+    return _drain_streams[key]
+
+
 def _target_points(target, device) -> torch.Tensor:
     """(n, 2) device tensor of the target's face centroids (the query points of
     CentroidLocatorRegridder and BarycentricInterpolator)."""
@@ -406,9 +422,12 @@ def _grid_from_dataset(ds: dict, prefix: str):
 class BaseRegridder(abc.ABC):
     _METHODS: Tuple[str, ...] = ()
     # face ranges a large target mesh is uploaded in (cumulative fractions): a small first
-    # range lets the first overlap job start early, larger later ranges keep the fixed cost
-    # of a job (0.3 ms) low; measured with scripts/e2e_timeline.py
-    _TARGET_CHUNKS = (0.1, 0.4, 1.0)
+    # range lets the first overlap job start early, a small last one leaves little to apply and
+    # bring down after the last job (regrid works range by range, _drain_ranges), ranges in
+    # between are large to keep the fixed cost of a job (0.3 ms under the upload) low;
+    # measured with scripts/e2e_timeline.py (profiles/r2_e2e_timeline_n1.txt)
+    _TARGET_CHUNKS = (0.15, 0.5, 0.85, 1.0)
+    _CHUNK_MIN_FACES = 1 << 20  # smaller target meshes go up in one piece
     _TARGET_AS_POINTS = False  # True: the weights need only the target's face centroids
 
     def __init__(self, source, target, tolerance: Optional[float] = None,
@@ -452,7 +471,7 @@ class BaseRegridder(abc.ABC):
         tgt_grid = self._target.to_unstructured().ugrid_topology
         if target_range is None or target_ids is not None:
             src_grid.prefetch(sharded=sharded_upload)
-            tgt_grid.prefetch(n_chunks=self._TARGET_CHUNKS if (tgt_grid.n_face >= (1 << 20) and target_ids is None) else 1,
+            tgt_grid.prefetch(n_chunks=self._TARGET_CHUNKS if (tgt_grid.n_face >= self._CHUNK_MIN_FACES and target_ids is None) else 1,
                               sharded=sharded_upload and target_ids is not None)
         else:
             # a shard: its (small) target range first, so that the clip box of the
@@ -517,7 +536,7 @@ class BaseRegridder(abc.ABC):
         A = pending.for_apply() if pending is not None else self._weights
         return self._regrid(source, A, self._rows())
 
-    def _upload_values(self, flat: torch.Tensor, dev) -> torch.Tensor:
+    def _upload_values(self, flat: torch.Tensor, dev, wait: bool = True):
         """Pinned host values -> device on the COPY stream (behind whatever mesh upload is
         still in flight there, next to the kernels that build the weights); 1/world per
         rank + an all-gather over NVLink for a regridder built with sharded_upload."""
@@ -533,10 +552,29 @@ class BaseRegridder(abc.ABC):
                 src = flat.to(dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(cs)
-        cur = torch.cuda.current_stream(dev)
-        cur.wait_event(ev)
-        src.record_stream(cur)
-        return src
+        if wait:
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ev)
+            src.record_stream(cur)
+        return src, ev
+
+    def _drain_ranges(self, pending, src: torch.Tensor, values_ready, res2d: torch.Tensor) -> None:
+        """The weights are being built range by range (a target mesh that is still arriving over
+        PCIe): apply and bring down the columns of every range as soon as its job is done, on a
+        high-priority side stream -- the device-to-host copy of the early ranges runs under the
+        jobs of the later ones, and only the last range's apply + copy is left at the end."""
+        dev = src.device
+        code, p = self._method
+        drain = _drain_stream(dev)
+        out_d = torch.empty((int(src.shape[0]), pending.n), dtype=torch.float64, device=dev)
+        drain.wait_event(values_ready)
+        with torch.cuda.stream(drain):
+            for b, e, done in pending.ranges:
+                drain.wait_event(done)
+                A = MatrixCSR(pending.data, pending.indices, pending.indptr[b: e + 1], e - b, pending.m, -1)
+                sparse.csr_apply(code, p, src, A, e - b, out=out_d[:, b:e], row_begin=b, row_end=e)
+                res2d[:, b:e].copy_(out_d[:, b:e], non_blocking=True)
+        drain.synchronize()
 
     def _regrid_array(self, source, out=None):
         source_grid = self._source
@@ -557,7 +595,17 @@ class BaseRegridder(abc.ABC):
         if is_tensor:
             flat = source.reshape((-1, source_grid.size))
             if host_tensor and flat.is_pinned() and flat.dtype == torch.float64 and flat.is_contiguous():
-                src = self._upload_values(flat, dev)
+                ranged = (pending is not None and len(pending.ranges) > 1 and out is None
+                          and isinstance(self, BaseOverlapRegridder) and self._target_range is None)
+                src, values_ready = self._upload_values(flat, dev, wait=not ranged)
+                if ranged:
+                    out_shape = first_dims_shape + tuple(self._target.shape)
+                    res = torch.empty(out_shape, dtype=torch.float64, pin_memory=True)
+                    self._drain_ranges(pending, src, values_ready, res.reshape(flat.shape[0], -1))
+                    if not pending.complete():
+                        _ = self._weights  # (rebuilt through the waiting path; apply again)
+                        return self._regrid_array(source, out)
+                    return res
             else:
                 src = flat.to(dev, non_blocking=True).to(torch.float64).contiguous()
         else:

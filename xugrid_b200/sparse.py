@@ -123,6 +123,9 @@ class PendingCSR:
         self._jobs, self._rebuild = list(jobs), rebuild
         self._final = None
         self._complete = None
+        # (row begin, row end, event recorded behind the job that writes those rows): what lets a
+        # consumer work on a range as soon as it is done, while later ranges are still being built
+        self.ranges = []
 
     def for_apply(self) -> "MatrixCSR":
         """What csr_apply needs (row pointer + arrays); nnz is not known yet (-1)."""
