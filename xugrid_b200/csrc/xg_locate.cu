@@ -273,16 +273,22 @@ k_intersect_edges(const LocateParams P, const double4 *__restrict__ edges, const
                 const int c = __ffs(m) - 1;
                 m &= m - 1;
                 const Box b = s_node[w][c];
-                if (boxes_touch(qb, b)) {
-                    const int64_t pos = c0 + c;
-                    double4 seg;
-                    if (cyrus_beck(e.x, e.y, e.z, e.w, poly + pos * k, nvert[pos] & 0x7f, &seg)) {
-                        const unsigned long long slot = atomicAdd(counter, 1ull);
-                        if (slot < cap) {
-                            edge_out[slot] = orig;
-                            face_out[slot] = perm[pos];
-                            xy_out[slot] = seg;
-                        }
+                const int64_t pos = c0 + c;
+                double4 seg;
+                bool hit = false;
+                if (boxes_touch(qb, b)) hit = cyrus_beck(e.x, e.y, e.z, e.w, poly + pos * k, nvert[pos] & 0x7f, &seg);
+                // one atomic per warp and child, not one per hit (the loop over m is warp-uniform)
+                const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                if (hm) {
+                    const int leader = __ffs(hm) - 1;
+                    unsigned long long base = 0;
+                    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(hm));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    const unsigned long long slot = base + __popc(hm & ((1u << lane) - 1u));
+                    if (hit && slot < cap) {
+                        edge_out[slot] = orig;
+                        face_out[slot] = perm[pos];
+                        xy_out[slot] = seg;
                     }
                 }
             }
