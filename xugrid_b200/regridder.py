@@ -426,7 +426,7 @@ class BaseRegridder(abc.ABC):
     # bring down after the last job (regrid works range by range, _drain_ranges), ranges in
     # between are large to keep the fixed cost of a job (0.3 ms under the upload) low;
     # measured with scripts/e2e_timeline.py (profiles/r2_e2e_timeline_n1.txt)
-    _TARGET_CHUNKS = (0.15, 0.5, 0.85, 1.0)
+    _TARGET_CHUNKS = (0.2, 0.85, 1.0)
     _CHUNK_MIN_FACES = 1 << 20  # smaller target meshes go up in one piece
     _TARGET_AS_POINTS = False  # True: the weights need only the target's face centroids
 
