@@ -189,3 +189,36 @@ def test_ranges_are_applied_and_downloaded_as_they_finish(xb, monkeypatch, bound
         # and once more on the settled weights (the ordinary path)
         again = r.regrid(values)
         assert torch.equal(again.view(torch.int64), out.view(torch.int64))
+
+
+def test_resident_range_is_built_as_two_chained_jobs(xb, monkeypatch):
+    """a large resident target range (a rank's shard, or a whole resident mesh) is split into two
+    chained jobs so that regrid() can bring the first part down under the second job; results
+    and out= semantics unchanged"""
+    from xugrid_b200 import regridder
+
+    sxy, sf = synthetic.jittered_lattice(150, 140, 51, "tri")
+    txy, tf = synthetic.jittered_lattice(160, 130, 52, "mixed")
+    src = xb.Ugrid2d(sxy[:, 0], sxy[:, 1], -1, sf)
+    tgt = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf)
+    values = torch.from_numpy(np.random.default_rng(10).random((2, len(sf)))).pin_memory()
+    good = xb.OverlapRegridder(src, tgt, method="mean").regrid(values)
+    monkeypatch.setattr(regridder.UnstructuredGrid2d, "_SPLIT_MIN_ROWS", 1000)
+    n_t = len(tf)
+    b, e = n_t // 5, n_t - n_t // 7
+    for rng in (None, (b, e)):
+        r = xb.OverlapRegridder(src, tgt, method="mean", target_range=rng)
+        pending = r.__dict__["_pending"]
+        assert len(pending.ranges) == 2 and pending.ranges[0][0] == 0 and pending.ranges[1][1] == pending.n
+        expect = good if rng is None else good[:, b:e]
+        out = r.regrid(values)
+        assert torch.equal(out.view(torch.int64), expect.contiguous().view(torch.int64))
+        # into a strided view of a larger host array (what a rank does with shared_host_array)
+        r2 = xb.OverlapRegridder(src, tgt, method="mean", target_range=rng)
+        big = torch.full((2, n_t + 10), -1.0, dtype=torch.float64).pin_memory()
+        lo = 3 if rng is None else b
+        view = big[:, lo: lo + expect.shape[1]]
+        got = r2.regrid(values, out=view)
+        assert got is view and torch.equal(view.contiguous().view(torch.int64), expect.contiguous().view(torch.int64))
+        assert bool((big[:, :lo] == -1.0).all()) and bool((big[:, lo + expect.shape[1]:] == -1.0).all())
+        assert r2._weights.nnz == r._weights.nnz

@@ -1132,7 +1132,7 @@ static int enqueue_move_rows(xg_overlap *job, const int64_t *d_indptr, int32_t *
 // buffers every attempt needs + the packed targets; returns the default arena capacity
 static int overlap_prepare(xg_overlap *job, const double *d_t_xy, const void *d_t_faces, int idx_bytes,
                            const int32_t *d_t_ids, int64_t n_t_mesh, int64_t t_begin, int64_t t_end,
-                           unsigned long long *cap_out) {
+                           unsigned long long *cap_out, bool may_sample) {
     const xg_index *source = job->src;
     cudaStream_t s = job->s;
     const int64_t n_t = job->n_t;
@@ -1172,7 +1172,9 @@ static int overlap_prepare(xg_overlap *job, const double *d_t_xy, const void *d_
     // its target mesh range by range while it is uploaded runs many such jobs, and the
     // sampling pass costs a host round trip each)
     const int64_t n_t_area = (source->n_face < source->n_face_mesh || d_t_ids) ? n_t : (n_t_mesh > n_t ? n_t_mesh : n_t);
-    if (source->n_face > 2 * n_t_area && n_t >= 32 * SAMPLE_STRIDE * 8) {
+    // (xg_overlap_run never samples -- that would be a host round trip: a job that is denser than
+    //  the default arena reports itself incomplete and its caller takes the waiting path)
+    if (may_sample && source->n_face > 2 * n_t_area && n_t >= 32 * SAMPLE_STRIDE * 8) {
         unsigned long long est = 0;
         rc = estimate_candidates(job, &est);  // (one host round trip)
         if (rc) return rc;
@@ -1222,7 +1224,7 @@ static int overlap_begin_impl(const xg_index *source, const double *d_t_xy, int6
             return XG_OK;
         }
         unsigned long long cap = 0;
-        rc = overlap_prepare(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, n_t_face, t_begin, t_end, &cap);
+        rc = overlap_prepare(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, n_t_face, t_begin, t_end, &cap, true);
         if (rc) goto fail;
         unsigned long long needed = 0;
         rc = overlap_attempt(job, cap, d_indptr, &needed);
@@ -1315,7 +1317,7 @@ extern "C" int xg_overlap_run(const xg_index *source, const double *d_t_xy, int6
         return XG_OK;
     }
     unsigned long long cap = 0;
-    rc = overlap_prepare(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, n_t_face, t_begin, t_end, &cap);
+    rc = overlap_prepare(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, n_t_face, t_begin, t_end, &cap, false);
     if (rc) return fail(rc);
     rc = overlap_enqueue(job, cap, d_indptr, chained != 0);
     if (rc) return fail(rc);

@@ -107,6 +107,13 @@ class UnstructuredGrid2d:
     # candidate pairs per target row the deferred path sizes its arrays for (what the
     # library's own pair arena holds by default: a job that needs more is redone)
     _ENTRIES_PER_ROW = 16
+    # a resident range of at least this many target rows is built as two chained jobs, so that
+    # regrid() can bring the first part down under the second job.  OFF by default: measured at
+    # N = 2 (5 M rows per rank) it gains nothing -- 9.59 vs 9.56 ms end to end: the second job
+    # runs 0.35 ms slower while the copy engine moves the first part (launch latency under
+    # PCIe traffic) and a job has 0.2 ms of fixed cost
+    _SPLIT_MIN_ROWS = 1 << 62
+    _SPLIT_AT = 0.8
 
     def overlap(self, other: "UnstructuredGrid2d", relative: bool,
                 target_range: Optional[Tuple[int, int]] = None,
@@ -189,6 +196,11 @@ class UnstructuredGrid2d:
             t_begin, t_end = (0, other.size) if target_range is None else target_range
             xy, faces = tgt.device_arrays(face_range=(t_begin, t_end))
             ranges = [(t_begin, t_end)]
+            if rows >= self._SPLIT_MIN_ROWS:
+                # two chained jobs: regrid() applies and brings down the first part under the
+                # second job (BaseRegridder._drain_ranges), so only a small tail follows the build
+                cut = t_begin + int(rows * self._SPLIT_AT)
+                ranges = [(t_begin, cut), (cut, t_end)]
         dev = xy.device
         if tree is None:
             sxy, sfaces = self.ugrid_topology.device_arrays()
@@ -196,7 +208,7 @@ class UnstructuredGrid2d:
                 ids = target_ids.to(dev)
                 tree = CellTree2d(sxy, sfaces, -1, device=dev, clip_target_ids=(xy, faces, ids))
             elif rows < other.size:
-                tree = CellTree2d(sxy, sfaces, -1, device=dev, clip_targets=(xy, faces, ranges[0][0], ranges[0][1]))
+                tree = CellTree2d(sxy, sfaces, -1, device=dev, clip_targets=(xy, faces, ranges[0][0], ranges[-1][1]))
             else:
                 tree = self.ugrid_topology.celltree
         self.last_tree = tree
@@ -595,13 +607,27 @@ class BaseRegridder(abc.ABC):
         if is_tensor:
             flat = source.reshape((-1, source_grid.size))
             if host_tensor and flat.is_pinned() and flat.dtype == torch.float64 and flat.is_contiguous():
-                ranged = (pending is not None and len(pending.ranges) > 1 and out is None
-                          and isinstance(self, BaseOverlapRegridder) and self._target_range is None)
+                ranged = (pending is not None and len(pending.ranges) > 1 and isinstance(self, BaseOverlapRegridder))
+                res = res2d = None
+                if ranged:
+                    out_shape = first_dims_shape + (tuple(self._target.shape) if self._target_range is None
+                                                    else (self._rows(),))
+                    if out is not None:
+                        if not isinstance(out, torch.Tensor) or out.is_cuda or tuple(out.shape) != tuple(out_shape) \
+                                or out.dtype != torch.float64:
+                            raise ValueError(f"out must be a float64 host tensor of shape {tuple(out_shape)}")
+                        res = out
+                    else:
+                        res = torch.empty(out_shape, dtype=torch.float64, pin_memory=True)
+                    if res.dim() == 2 and res.shape[0] == flat.shape[0]:
+                        res2d = res  # (e.g. the columns of a shared host array: strided, fine)
+                    elif res.is_contiguous():
+                        res2d = res.view(flat.shape[0], -1)
+                    else:
+                        ranged = False
                 src, values_ready = self._upload_values(flat, dev, wait=not ranged)
                 if ranged:
-                    out_shape = first_dims_shape + tuple(self._target.shape)
-                    res = torch.empty(out_shape, dtype=torch.float64, pin_memory=True)
-                    self._drain_ranges(pending, src, values_ready, res.reshape(flat.shape[0], -1))
+                    self._drain_ranges(pending, src, values_ready, res2d)
                     if not pending.complete():
                         _ = self._weights  # (rebuilt through the waiting path; apply again)
                         return self._regrid_array(source, out)
