@@ -160,10 +160,10 @@ int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32_t *d_indic
  * apply and the copies behind it (the reference has no counterpart: numba code is
  * synchronous).  d_t_ids may be NULL (targets = faces [t_begin, t_end)) or a face list
  * (targets = d_t_ids[t_begin .. t_end)).  d_indptr receives the rows + 1 row pointers.
- * chained != 0: d_indptr[0] already holds, ON THE DEVICE, the offset of this job's first
+ * flags & XG_RUN_CHAINED: d_indptr[0] already holds, ON THE DEVICE, the offset of this job's first
  * entry -- pass the address of the last row pointer of the job before it and the jobs of
  * consecutive target ranges fill ONE CSR matrix (how the regridders consume a target mesh
- * that is still being uploaded range by range); chained == 0: the matrix starts at 0.
+ * that is still being uploaded range by range); otherwise the matrix starts at 0.
  * Rows are written sorted by ascending source index, as by xg_overlap_finish.
  * Nothing is waited for.  xg_overlap_result waits for the job, returns its nnz, the row
  * pointer behind its last row and whether it is complete: a job whose candidate arena or
@@ -171,9 +171,14 @@ int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32_t *d_indic
  * was written out of bounds) and must be redone with xg_overlap_begin/finish, which
  * re-sizes.  xg_overlap_stats / _timings are valid after xg_overlap_result; release the
  * job with xg_overlap_abort. */
+#define XG_RUN_CHAINED 1 /* d_indptr[0] holds the offset of the job's first entry (see above) */
+#define XG_RUN_GRAPH 2   /* launch the job as ONE CUDA graph: its ~30 small launches otherwise cost
+                          * 25-40 us each while a mesh upload saturates PCIe; no per-phase timings then
+                          * (stats[7] = 1 when the job really went out as a graph: a scratch block that
+                          * is not in the library's cache yet makes it fall back to direct launches) */
 int xg_overlap_run(const xg_index *source, const double *d_t_xy, int64_t n_t_node,
                    const void *d_t_faces, int idx_bytes, int64_t n_t_face, int k_t,
-                   const int32_t *d_t_ids, int64_t t_begin, int64_t t_end, int chained,
+                   const int32_t *d_t_ids, int64_t t_begin, int64_t t_end, int flags,
                    int64_t *d_indptr, int32_t *d_indices, double *d_area, int64_t entry_cap,
                    int relative, void *stream, xg_overlap **job);
 int xg_overlap_result(xg_overlap *job, int64_t *h_nnz, int64_t *h_nnz_end, int *h_complete);

@@ -64,5 +64,6 @@ for nchunk in chunks:
         print(f"  {t:8.3f} ms  {name}")
     if pend is not None:
         pend.complete()
+        print("  jobs launched as graphs:", [getattr(j, "launched_as_graph", None) for j in getattr(pend, "_all_jobs", [])])
         for j, ph in enumerate(pend.job_phase_ms):
             print(f"  job {j}: " + "  ".join(f"{k} {v:.3f}" for k, v in ph.items()) + f"  sum {sum(ph.values()):.3f}")

@@ -222,3 +222,30 @@ def test_resident_range_is_built_as_two_chained_jobs(xb, monkeypatch):
         assert got is view and torch.equal(view.contiguous().view(torch.int64), expect.contiguous().view(torch.int64))
         assert bool((big[:, :lo] == -1.0).all()) and bool((big[:, lo + expect.shape[1]:] == -1.0).all())
         assert r2._weights.nnz == r._weights.nnz
+
+
+def test_job_as_one_cuda_graph(xb):
+    """XG_RUN_GRAPH: same CSR; the first call may fall back to direct launches (scratch cache
+    cold), the repeats go out as graphs"""
+    sxy, sf, txy, tf = _meshes()
+    dev = torch.device("cuda", 0)
+    tree = xb.CellTree2d(sxy, sf)
+    dxy, dtf = torch.from_numpy(txy).to(dev), torch.from_numpy(tf).to(dev)
+    n_t = len(tf)
+    ip0, ix0, ar0 = tree.intersect_faces_csr(dxy, dtf)
+    as_graph = []
+    for rep in range(4):
+        indptr = torch.full((n_t + 1,), -7, dtype=torch.int64, device=dev)
+        indices = torch.empty(16 * n_t, dtype=torch.int32, device=dev)
+        area = torch.empty(16 * n_t, dtype=torch.float64, device=dev)
+        cut = n_t // 3
+        jobs = [tree.intersect_faces_into(dxy, dtf, indptr[: cut + 1], indices, area, t_begin=0, t_end=cut, graph=True),
+                tree.intersect_faces_into(dxy, dtf, indptr[cut:], indices, area, t_begin=cut, t_end=n_t, chained=True, graph=True)]
+        end = 0
+        for j in jobs:
+            _, end, ok = j.result()
+            assert ok
+            as_graph.append(j.launched_as_graph)
+        assert end == int(ip0[-1]) and torch.equal(indptr, ip0) and torch.equal(indices[:end], ix0)
+        assert torch.equal(area[:end].view(torch.int64), ar0.view(torch.int64))
+    assert all(as_graph[-2:]), as_graph

@@ -99,6 +99,7 @@ class PendingOverlap:
                 st = (ctypes.c_int64 * 8)()
                 _native.check(L.xg_overlap_stats(self._job, st))
                 self.stats = OverlapStats(*[int(st[i]) for i in range(7)])
+                self.launched_as_graph = bool(st[7])
                 ms = (ctypes.c_double * 8)()
                 _native.check(L.xg_overlap_timings(self._job, ms))
                 self.phase_ms = dict(zip(PHASES, [float(ms[i]) for i in range(len(PHASES))]))
@@ -289,6 +290,7 @@ class CellTree2d:
         relative: bool = False,
         ids: Optional[torch.Tensor] = None,
         chained: bool = False,
+        graph: bool = False,
     ) -> "PendingOverlap":
         """
         The same CSR rows written into arrays the caller sized by an upper bound, with
@@ -296,8 +298,11 @@ class CellTree2d:
         row pointer these target rows own, ``indices`` / ``area`` the whole entry arrays.
         ``chained=True``: ``indptr[0]`` already holds (on the device) the offset of the first
         entry, i.e. the last row pointer of the rows before -- consecutive target ranges
-        fill one matrix.  Returns a handle; ``.result()`` waits and tells whether the job
-        is complete (arena and arrays were large enough).
+        fill one matrix.  ``graph=True``: the job goes out as one CUDA graph launch (what a
+        regridder asks for: under a mesh upload every small launch of a job is slowed down by
+        the traffic on the PCIe link); no per-phase timings then.  Returns a handle;
+        ``.result()`` waits and tells whether the job is complete (arena and arrays were large
+        enough).
         """
         L = _native.lib()
         with torch.cuda.device(self.device):
@@ -314,7 +319,7 @@ class CellTree2d:
                 L.xg_overlap_run(
                     self._h, _native.ptr(vertices, torch.float64), int(vertices.shape[0]), _native.ptr(faces),
                     faces.element_size(), n_t, k_t, _native.ptr(ids, torch.int32) if ids is not None else None,
-                    t_begin, t_end, 1 if chained else 0, _native.ptr(indptr, torch.int64),
+                    t_begin, t_end, (1 if chained else 0) | (2 if graph else 0), _native.ptr(indptr, torch.int64),
                     _native.ptr(indices, torch.int32), _native.ptr(area, torch.float64), int(area.numel()),
                     1 if relative else 0, _native.stream_ptr(), ctypes.byref(job),
                 )

@@ -111,6 +111,8 @@ inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // synchronisation happened since the last free (measured: 0.8 ms -> 7 ms).
 cudaError_t scratch_alloc(void **p, size_t *cap, size_t bytes, cudaStream_t s);
 void scratch_free(void *p, size_t cap, cudaStream_t s);
+// while set (per host thread), a request that the cache cannot serve fails instead of allocating
+void scratch_set_capturing(bool on);
 
 // stream-ordered scratch allocation that frees itself
 struct DevBuf {
@@ -130,6 +132,11 @@ struct DevBuf {
     void release() {
         if (p) scratch_free(p, cap, s);
         p = nullptr;
+    }
+    // keeps a block that is large enough
+    cudaError_t ensure(size_t n, cudaStream_t stream) {
+        if (p && cap >= (n ? n : 16) && s == stream) { bytes = n ? n : 16; return cudaSuccess; }
+        return alloc(n, stream);
     }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };

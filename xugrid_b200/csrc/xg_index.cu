@@ -71,6 +71,9 @@ static size_t round_size(size_t n) {
     return (n + g - 1) / g * g;
 }
 
+static thread_local bool t_capturing = false;
+void scratch_set_capturing(bool on) { t_capturing = on; }
+
 cudaError_t scratch_alloc(void **p, size_t *cap, size_t bytes, cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -92,6 +95,9 @@ cudaError_t scratch_alloc(void **p, size_t *cap, size_t bytes, cudaStream_t s) {
             return cudaSuccess;
         }
     }
+    // while a job is being recorded into a CUDA graph nothing may be allocated: the caller gives
+    // the capture up, runs directly (which fills the cache) and captures the next time
+    if (t_capturing) return cudaErrorStreamCaptureUnsupported;
     *cap = want;
     return cudaMallocAsync(p, want, s);
 }
@@ -498,10 +504,22 @@ static void ensure_pool_config() {
     configured.push_back(dev);
 }
 
+size_t pack_sort_tmp_bytes(int64_t n) {
+    size_t tb = 0;
+    if (n <= 0) return 16;
+    // (the temporary storage of the sort does not depend on the bit range)
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int32_t *)nullptr,
+                                    (int32_t *)nullptr, n, 0, 32, (cudaStream_t)0);
+    return tb ? tb : 16;
+}
+
 int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_begin,
               int64_t f_end, int k, const double *d_frame, unsigned long long *d_diag2,
               PackedMesh *out, cudaStream_t s, const double *d_clip_box, unsigned long long *d_kept,
-              const int32_t *d_face_ids, int64_t n_node) {
+              const int32_t *d_face_ids, int64_t n_node, cudaStream_t alloc_stream, const PackScratch *scratch) {
+    // alloc_stream: the stream the scratch blocks are ordered on (differs from s only while s is
+    // a capture stream: the recorded work will run on alloc_stream)
+    cudaStream_t as = alloc_stream ? alloc_stream : s;
     ensure_pool_config();
     const int64_t n = f_end - f_begin;
     out->n = n;
@@ -511,21 +529,28 @@ int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_
     const double2 *xy = reinterpret_cast<const double2 *>(d_xy);
     DevBuf keys_in, keys_out, ids_in, tmp, outcode;
     if (clip && n_node > 0) {
-        XG_CUDA(outcode.alloc((size_t)n_node, s));
+        XG_CUDA(outcode.alloc((size_t)n_node, as));
         k_node_outcodes<<<(unsigned)div_up(n_node, 256), 256, 0, s>>>(xy, n_node, clip, outcode.as<uint8_t>());
         XG_CHECK_LAUNCH();
     }
-    XG_CUDA(keys_in.alloc(sizeof(uint32_t) * (size_t)n, s));
-    XG_CUDA(keys_out.alloc(sizeof(uint32_t) * (size_t)n, s));
-    XG_CUDA(ids_in.alloc(sizeof(int32_t) * (size_t)n, s));
+    uint32_t *k_in, *k_out;
+    int32_t *i_in;
+    if (scratch) {
+        k_in = scratch->keys_in; k_out = scratch->keys_out; i_in = scratch->ids_in;
+    } else {
+        XG_CUDA(keys_in.alloc(sizeof(uint32_t) * (size_t)n, as));
+        XG_CUDA(keys_out.alloc(sizeof(uint32_t) * (size_t)n, as));
+        XG_CUDA(ids_in.alloc(sizeof(int32_t) * (size_t)n, as));
+        k_in = keys_in.as<uint32_t>(); k_out = keys_out.as<uint32_t>(); i_in = ids_in.as<int32_t>();
+    }
     int rc;
     if (idx_bytes == 4)
         rc = launch_face_keys<int32_t>(xy, (const int32_t *)d_faces, f_begin, n, k, d_frame,
-                                       keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, clip, d_kept,
+                                       k_in, i_in, d_diag2, clip, d_kept,
                                        d_face_ids, s, outcode.as<uint8_t>());
     else
         rc = launch_face_keys<int64_t>(xy, (const int64_t *)d_faces, f_begin, n, k, d_frame,
-                                       keys_in.as<uint32_t>(), ids_in.as<int32_t>(), d_diag2, clip, d_kept,
+                                       k_in, i_in, d_diag2, clip, d_kept,
                                        d_face_ids, s, outcode.as<uint8_t>());
     if (rc) return rc;
     int64_t n_pack = n;
@@ -550,13 +575,15 @@ int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_
         while (bits < 32 && ((int64_t)1 << bits) < n_pack) bits += 8;
         const int begin_bit = 32 - bits;
         size_t tb = 0;
-        XG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in.as<uint32_t>(),
-                                                keys_out.as<uint32_t>(), ids_in.as<int32_t>(),
-                                                out->perm, n_pack, begin_bit, 32, s));
-        XG_CUDA(tmp.alloc(tb, s));
-        XG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys_in.as<uint32_t>(),
-                                                keys_out.as<uint32_t>(), ids_in.as<int32_t>(),
-                                                out->perm, n_pack, begin_bit, 32, s));
+        XG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, i_in, out->perm, n_pack, begin_bit, 32, s));
+        void *sort_tmp;
+        if (scratch && scratch->sort_tmp_bytes >= tb) {
+            sort_tmp = scratch->sort_tmp;
+        } else {
+            XG_CUDA(tmp.alloc(tb, as));
+            sort_tmp = tmp.p;
+        }
+        XG_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, tb, k_in, k_out, i_in, out->perm, n_pack, begin_bit, 32, s));
     }
     if (idx_bytes == 4)
         rc = launch_pack<int32_t>(xy, (const int32_t *)d_faces, k, out->perm, n_pack, out->box,

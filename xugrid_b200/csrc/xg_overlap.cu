@@ -835,7 +835,14 @@ static int launch_clip(const ClipArgs &A, cudaStream_t s) {
     // (the filter keeps its own block size: it is tuned separately from the clip kernel)
     constexpr int SBT = (KT + KS <= 8) ? 256 : BT;
     const size_t smem_sat = sizeof(double2) * 2 * (size_t)(KT + KS) * SBT;  // two staged pairs per thread
-    XG_CUDA(cudaFuncSetAttribute(k_sat<KT, KS, SBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sat));
+    // (attributes are set once per device and instantiation: nothing but launches while a job is
+    //  being captured into a graph)
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    XG_CUDA(cudaGetDevice(&dev));
+    const bool set_attr = dev < 0 || dev >= 64 || !attr_set[dev];
+    if (set_attr)
+        XG_CUDA(cudaFuncSetAttribute(k_sat<KT, KS, SBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sat));
     XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sat<KT, KS, SBT>, SBT, smem_sat));
     if (per_sm < 1) per_sm = 1;
     k_sat<KT, KS, SBT><<<num_sms() * per_sm, SBT, smem_sat, s>>>(A.pairs, A.cap, (const double2 *)A.tpoly, A.tnv, A.kt,
@@ -844,7 +851,10 @@ static int launch_clip(const ClipArgs &A, cudaStream_t s) {
     if (A.between) XG_CUDA(cudaEventRecord(A.between, s));
     size_t smem = sizeof(double2) * 3 * (size_t)(KT + KS) * BT;  // 2 ping-pong lists + 1 staged pair
     auto kern = k_clip_survivors<KT, KS, BT, MINB>;
-    XG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (set_attr) {
+        XG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
     XG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem));
     if (per_sm < 1) per_sm = 1;
     kern<<<num_sms() * per_sm, BT, smem, s>>>(A.surv, A.ctr, (const double2 *)A.tpoly, A.tnv, A.kt,
@@ -866,6 +876,8 @@ struct xg_overlap {
     cudaStream_t s = nullptr;
     // device buffers
     DevBuf tperm, tbox, tpoly, tnv, pairs, surv, prov_col, cnt, prov_ptr, scan_tmp, ctr;
+    DevBuf pk_keys_in, pk_keys_out, pk_ids, pk_tmp;  // scratch of the target packing
+    PackScratch pk;
     size_t scan_tmp_bytes = 0;
     int64_t h_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool stats_valid = false;
@@ -880,6 +892,11 @@ struct xg_overlap {
     // xg_overlap_run: nothing is waited for until xg_overlap_result
     bool deferred = false, empty = false;
     cudaEvent_t done = nullptr;
+    // xg_overlap_run with XG_RUN_GRAPH: the whole job is one CUDA graph launch
+    bool timing = true;
+    cudaStream_t ls = nullptr;  // where the job's operations are issued: s, or the capture stream
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
     xg_overlap() { for (int i = 0; i <= XG_N_PHASES; ++i) ev[i] = nullptr; }
     ~xg_overlap() {
         for (int i = 0; i <= XG_N_PHASES; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
@@ -888,20 +905,25 @@ struct xg_overlap {
             if (h_ctr && !stats_valid) cudaEventSynchronize(done);
             cudaEventDestroy(done);
         }
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);  // (after the wait above: never while in flight)
+        if (graph) cudaGraphDestroy(graph);
         if (h_ctr) pinned_slot_release(h_ctr);
     }
     void release_scratch() {
         tperm.release(); tbox.release(); tpoly.release(); tnv.release(); pairs.release(); surv.release();
         prov_col.release(); cnt.release(); prov_ptr.release(); scan_tmp.release(); ctr.release();
+        pk_keys_in.release(); pk_keys_out.release(); pk_ids.release(); pk_tmp.release();
     }
     cudaError_t mark() {
+        if (!timing) { ++n_ev; return cudaSuccess; }  // (a captured job records no phase events)
         if (!ev[n_ev]) {
             cudaError_t e = cudaEventCreate(&ev[n_ev]);
             if (e != cudaSuccess) return e;
         }
-        return cudaEventRecord(ev[n_ev++], s);
+        return cudaEventRecord(ev[n_ev++], ls);
     }
     void collect() {
+        if (!timing) return;
         for (int i = 0; i + 1 < n_ev; ++i) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) h_ms[i] = ms;
@@ -958,7 +980,8 @@ k_fill_from(int64_t *__restrict__ dst, int64_t n, const int64_t *__restrict__ sr
 // d_indptr[0] on the device (the last row pointer of the job before it) instead of 0.
 static int overlap_enqueue(xg_overlap *job, unsigned long long cap, int64_t *d_indptr, bool chained) {
     const xg_index *source = job->src;
-    cudaStream_t s = job->s;
+    cudaStream_t s = job->ls;        // operations
+    cudaStream_t as = job->s;        // the stream the scratch blocks belong to (where the job executes)
     const int64_t n_t = job->n_t;
     const int k_t = job->k_t, ks = source->k;
     job->n_ev = 1;  // keep ev[0] (pack start), re-record the rest
@@ -968,10 +991,11 @@ static int overlap_enqueue(xg_overlap *job, unsigned long long cap, int64_t *d_i
     if (chained)
         XG_CUDA(cudaMemcpyAsync(job->ctr.as<unsigned long long>() + CTR_BASE, d_indptr, sizeof(int64_t),
                                 cudaMemcpyDeviceToDevice, s));
-    XG_CUDA(job->pairs.alloc(sizeof(int2) * (size_t)cap, s));
-    // (+ the unused tails of the last survivor windows: at most 8 blocks of 8 warps per SM)
-    XG_CUDA(job->surv.alloc(sizeof(int2) * ((size_t)cap + (size_t)num_sms() * 64 * SAT_WIN), s));
-    XG_CUDA(job->prov_col.alloc(sizeof(int32_t) * (size_t)cap, s));
+    // (arenas: kept when overlap_alloc sized them already; + the unused tails of the last survivor
+    //  windows: at most 8 blocks of 8 warps per SM)
+    XG_CUDA(job->pairs.ensure(sizeof(int2) * (size_t)cap, as));
+    XG_CUDA(job->surv.ensure(sizeof(int2) * ((size_t)cap + (size_t)num_sms() * 64 * SAT_WIN), as));
+    XG_CUDA(job->prov_col.ensure(sizeof(int32_t) * (size_t)cap, as));
     // cnt = [cand_cnt | fill_cnt | row_cnt], (n_t + 1) int32 each
     XG_CUDA(cudaMemsetAsync(job->cnt.p, 0, sizeof(int32_t) * 2 * (size_t)(n_t + 1), s));
     int32_t *cand_cnt = job->cnt.as<int32_t>(), *fill_cnt = cand_cnt + (n_t + 1), *row_cnt = fill_cnt + (n_t + 1);
@@ -1000,8 +1024,13 @@ static int overlap_enqueue(xg_overlap *job, unsigned long long cap, int64_t *d_i
     A.prov_ptr = job->prov_ptr.as<int64_t>();
     A.prov_col = job->prov_col.as<int32_t>();
     A.prov_val = job->pairs.as<double>();  // the candidate arena is dead once k_sat has run (same 8 B per entry)
-    if (!job->ev[job->n_ev]) XG_CUDA(cudaEventCreate(&job->ev[job->n_ev]));
-    A.between = job->ev[job->n_ev++];  // XG_PHASE_CLIP starts between the two kernels
+    if (job->timing) {
+        if (!job->ev[job->n_ev]) XG_CUDA(cudaEventCreate(&job->ev[job->n_ev]));
+        A.between = job->ev[job->n_ev++];  // XG_PHASE_CLIP starts between the two kernels
+    } else {
+        A.between = nullptr;
+        ++job->n_ev;
+    }
     int rc;
     // (block size / min-blocks variants 256x2..4, 128x6..8 were measured: 3.30-3.87 ms, 256x3 best)
 #ifndef XG_CLIP_BT
@@ -1041,7 +1070,7 @@ static int overlap_request_counters(xg_overlap *job) {
         if (!job->h_ctr) { set_error("overlap: no pinned host memory"); return XG_ERR_NOMEM; }
     }
     static_assert(sizeof(unsigned long long) * CTR_N <= 128, "a pinned slot holds 128 bytes");
-    XG_CUDA(cudaMemcpyAsync(job->h_ctr, job->ctr.p, sizeof(unsigned long long) * CTR_N, cudaMemcpyDeviceToHost, job->s));
+    XG_CUDA(cudaMemcpyAsync(job->h_ctr, job->ctr.p, sizeof(unsigned long long) * CTR_N, cudaMemcpyDeviceToHost, job->ls));
     XG_CUDA(job->mark());  // end
     return XG_OK;
 }
@@ -1130,14 +1159,18 @@ static int enqueue_move_rows(xg_overlap *job, const int64_t *d_indptr, int32_t *
 }
 
 // buffers every attempt needs + the packed targets; returns the default arena capacity
-static int overlap_prepare(xg_overlap *job, const double *d_t_xy, const void *d_t_faces, int idx_bytes,
-                           const int32_t *d_t_ids, int64_t n_t_mesh, int64_t t_begin, int64_t t_end,
-                           unsigned long long *cap_out, bool may_sample) {
-    const xg_index *source = job->src;
+// Every scratch buffer of a job is allocated up front (nothing is allocated while a job is being
+// recorded into a graph): job buffers, the scratch of the target packing, and -- for a job that
+// will not be re-sized (xg_overlap_run) -- the arenas of the default capacity.
+static unsigned long long default_arena(int64_t n_t) {
+    unsigned long long cap = (unsigned long long)n_t * PAIRS_PER_TARGET_GUESS;
+    return cap < 65536 ? 65536 : cap;
+}
+
+static int overlap_alloc(xg_overlap *job, bool with_arenas) {
     cudaStream_t s = job->s;
     const int64_t n_t = job->n_t;
     const int k_t = job->k_t;
-    XG_CUDA(job->mark());  // XG_PHASE_PACK
     XG_CUDA(job->ctr.alloc(sizeof(unsigned long long) * CTR_N, s));
     XG_CUDA(job->tperm.alloc(sizeof(int32_t) * (size_t)n_t, s));
     XG_CUDA(job->tbox.alloc(sizeof(Box) * (size_t)n_t, s));
@@ -1156,27 +1189,48 @@ static int overlap_prepare(xg_overlap *job, const double *d_t_xy, const void *d_
         job->scan_tmp_bytes = tb_sum > tb_scan ? tb_sum : tb_scan;
         XG_CUDA(job->scan_tmp.alloc(job->scan_tmp_bytes, s));
     }
+    // scratch of pack_mesh (keys in / out, ids, sort)
+    XG_CUDA(job->pk_keys_in.alloc(sizeof(uint32_t) * (size_t)n_t, s));
+    XG_CUDA(job->pk_keys_out.alloc(sizeof(uint32_t) * (size_t)n_t, s));
+    XG_CUDA(job->pk_ids.alloc(sizeof(int32_t) * (size_t)n_t, s));
+    job->pk.sort_tmp_bytes = pack_sort_tmp_bytes(n_t);
+    XG_CUDA(job->pk_tmp.alloc(job->pk.sort_tmp_bytes, s));
+    job->pk.keys_in = job->pk_keys_in.as<uint32_t>(); job->pk.keys_out = job->pk_keys_out.as<uint32_t>();
+    job->pk.ids_in = job->pk_ids.as<int32_t>(); job->pk.sort_tmp = job->pk_tmp.p;
+    if (with_arenas) {
+        const unsigned long long cap = default_arena(n_t);
+        XG_CUDA(job->pairs.alloc(sizeof(int2) * (size_t)cap, s));
+        XG_CUDA(job->surv.alloc(sizeof(int2) * ((size_t)cap + (size_t)num_sms() * 64 * SAT_WIN), s));
+        XG_CUDA(job->prov_col.alloc(sizeof(int32_t) * (size_t)cap, s));
+    }
+    return XG_OK;
+}
+
+// targets of the job in curve order (launches only)
+static int overlap_pack(xg_overlap *job, const double *d_t_xy, const void *d_t_faces, int idx_bytes,
+                        const int32_t *d_t_ids, int64_t t_begin, int64_t t_end) {
+    XG_CUDA(job->mark());  // XG_PHASE_PACK
     PackedMesh pm;
     pm.perm = job->tperm.as<int32_t>(); pm.box = job->tbox.as<Box>();
     pm.poly = job->tpoly.as<double>(); pm.nvert = job->tnv.as<uint8_t>();
-    int rc = pack_mesh(d_t_xy, d_t_faces, idx_bytes, t_begin, t_end, k_t, source->d_frame, nullptr, &pm, s,
-                       nullptr, nullptr, d_t_ids);
-    if (rc) return rc;
     // (with a face list, tperm holds list positions t_begin + i: rows stay tperm - t_begin)
+    return pack_mesh(d_t_xy, d_t_faces, idx_bytes, t_begin, t_end, job->k_t, job->src->d_frame, nullptr, &pm, job->ls,
+                     nullptr, nullptr, d_t_ids, 0, job->s, &job->pk);
+}
 
-    unsigned long long cap = (unsigned long long)n_t * PAIRS_PER_TARGET_GUESS;
-    if (cap < 65536) cap = 65536;
+// arena capacity of the waiting path: the default, or a sampled estimate when the source is
+// much finer than the targets
+static int overlap_capacity(xg_overlap *job, const int32_t *d_t_ids, int64_t n_t_mesh, unsigned long long *cap_out) {
+    const xg_index *source = job->src;
+    const int64_t n_t = job->n_t;
+    unsigned long long cap = default_arena(n_t);
     // "source much finer than the targets" compares meshes over the same area: an index
     // culled to these targets against the targets, a whole-mesh index against the whole
-    // target mesh -- not against the few rows of one range of it (a regridder that consumes
-    // its target mesh range by range while it is uploaded runs many such jobs, and the
-    // sampling pass costs a host round trip each)
+    // target mesh -- not against the few rows of one range of it
     const int64_t n_t_area = (source->n_face < source->n_face_mesh || d_t_ids) ? n_t : (n_t_mesh > n_t ? n_t_mesh : n_t);
-    // (xg_overlap_run never samples -- that would be a host round trip: a job that is denser than
-    //  the default arena reports itself incomplete and its caller takes the waiting path)
-    if (may_sample && source->n_face > 2 * n_t_area && n_t >= 32 * SAMPLE_STRIDE * 8) {
+    if (source->n_face > 2 * n_t_area && n_t >= 32 * SAMPLE_STRIDE * 8) {
         unsigned long long est = 0;
-        rc = estimate_candidates(job, &est);  // (one host round trip)
+        const int rc = estimate_candidates(job, &est);  // (one host round trip)
         if (rc) return rc;
         if (est > cap) cap = est;
     }
@@ -1211,7 +1265,7 @@ static int overlap_begin_impl(const xg_index *source, const double *d_t_xy, int6
     index_note_use(source, s);
     const int64_t n_t = t_end - t_begin;
     xg_overlap *job = new xg_overlap();
-    job->src = source; job->t_begin = t_begin; job->n_t = n_t; job->k_t = k_t; job->s = s;
+    job->src = source; job->t_begin = t_begin; job->n_t = n_t; job->k_t = k_t; job->s = s; job->ls = s;
 #define OV_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = cuda_fail(e__, #call, __FILE__, __LINE__); goto fail; } } while (0)
     {
         if (n_t == 0 || source->n_face == 0) {
@@ -1224,7 +1278,11 @@ static int overlap_begin_impl(const xg_index *source, const double *d_t_xy, int6
             return XG_OK;
         }
         unsigned long long cap = 0;
-        rc = overlap_prepare(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, n_t_face, t_begin, t_end, &cap, true);
+        rc = overlap_alloc(job, false);
+        if (rc) goto fail;
+        rc = overlap_pack(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, t_begin, t_end);
+        if (rc) goto fail;
+        rc = overlap_capacity(job, d_t_ids, n_t_face, &cap);
         if (rc) goto fail;
         unsigned long long needed = 0;
         rc = overlap_attempt(job, cap, d_indptr, &needed);
@@ -1282,14 +1340,39 @@ extern "C" int xg_overlap_finish(xg_overlap *job, const int64_t *d_indptr, int32
     return rc;
 }
 
+// a private stream per host thread on which jobs are recorded into graphs (never executes anything)
+static cudaStream_t capture_stream() {
+    static thread_local cudaStream_t cs[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!cs[dev] && cudaStreamCreateWithFlags(&cs[dev], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        cs[dev] = nullptr;
+    }
+    return cs[dev];
+}
+
 // The whole job enqueued at once: no host round trip between the walk and the caller's
 // CSR arrays, which are sized by an upper bound instead of the nnz read-back.
 extern "C" int xg_overlap_run(const xg_index *source, const double *d_t_xy, int64_t n_t_node,
                               const void *d_t_faces, int idx_bytes, int64_t n_t_face, int k_t,
-                              const int32_t *d_t_ids, int64_t t_begin, int64_t t_end, int chained,
+                              const int32_t *d_t_ids, int64_t t_begin, int64_t t_end, int flags,
                               int64_t *d_indptr, int32_t *d_indices, double *d_area, int64_t entry_cap,
                               int relative, void *stream, xg_overlap **job_out) {
     (void)n_t_node;
+    const int chained = flags & XG_RUN_CHAINED;
+    // One CUDA graph per job: its ~30 small launches (memsets, key / sort / pack of the targets,
+    // scans, row movers) cost 25-40 us EACH while the copy engine saturates PCIe with the rest of
+    // a mesh upload -- the front end fetches every launch over the same link -- which made a
+    // 1 M-row job 0.5 ms slower under an upload than on resident data.  Captured, the job is one
+    // submission.  Capture needs every scratch block to come from the cache: a miss ends the
+    // capture and the job is enqueued directly (that fills the cache for the next time).
+    bool as_graph = (flags & XG_RUN_GRAPH) != 0;
+    {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (as_graph && (cudaStreamIsCapturing((cudaStream_t)stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone))
+            as_graph = false;  // (the caller is capturing already)
+    }
     if (!job_out || !d_indices || !d_area || entry_cap < 0) { set_error("xg_overlap_run: invalid argument"); return XG_ERR_INVALID; }
     *job_out = nullptr;
     int rc = overlap_check_args("xg_overlap_run", source, d_indptr, d_t_ids, idx_bytes, n_t_face, k_t, t_begin, t_end);
@@ -1298,11 +1381,26 @@ extern "C" int xg_overlap_run(const xg_index *source, const double *d_t_xy, int6
     index_note_use(source, s);
     const int64_t n_t = t_end - t_begin;
     xg_overlap *job = new xg_overlap();
-    job->src = source; job->t_begin = t_begin; job->n_t = n_t; job->k_t = k_t; job->s = s;
+    job->src = source; job->t_begin = t_begin; job->n_t = n_t; job->k_t = k_t; job->s = s; job->ls = s;
     job->deferred = true;
     job->h_stats[0] = n_t;
     job->h_stats[6] = 1;
-    auto fail = [&](int code) { delete job; return code; };
+    bool capturing = false;
+    auto fail = [&](int code) {
+        if (capturing) {
+            if (getenv("XG_GRAPH_DEBUG")) fprintf(stderr, "[xg] capture of an overlap job given up (rc %d): %s\n", code, xg_last_error_string());
+            scratch_set_capturing(false);
+            cudaGraph_t g = nullptr;
+            cudaStreamEndCapture(job->ls, &g);  // (invalidated by the error: nothing was enqueued)
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+        }
+        delete job;
+        if (capturing)  // once more, enqueued directly
+            return xg_overlap_run(source, d_t_xy, n_t_node, d_t_faces, idx_bytes, n_t_face, k_t, d_t_ids, t_begin, t_end,
+                                  flags & ~XG_RUN_GRAPH, d_indptr, d_indices, d_area, entry_cap, relative, stream, job_out);
+        return code;
+    };
     if (n_t == 0 || source->n_face == 0) {
         // every row is empty: all row pointers = the job's first entry
         cudaError_t e = cudaSuccess;
@@ -1316,15 +1414,54 @@ extern "C" int xg_overlap_run(const xg_index *source, const double *d_t_xy, int6
         *job_out = job;
         return XG_OK;
     }
-    unsigned long long cap = 0;
-    rc = overlap_prepare(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, n_t_face, t_begin, t_end, &cap, false);
+    rc = overlap_alloc(job, true);
+    if (rc) return fail(rc);
+    if (as_graph) {
+        job->h_ctr = pinned_slot_acquire();  // (no host allocation inside the capture either)
+        if (!job->h_ctr) { set_error("overlap: no pinned host memory"); return fail(XG_ERR_NOMEM); }
+        // (the caller's stream may be the legacy default stream, which cannot be captured: the job
+        //  is recorded on a private stream and the graph launched on the caller's)
+        cudaStream_t cs = capture_stream();
+        if (cs && cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            capturing = true;
+            job->timing = false;
+            job->ls = cs;
+            scratch_set_capturing(true);
+        } else {
+            cudaGetLastError();
+            as_graph = false;
+        }
+    }
+    // (never sampled -- that would be a host round trip: a job that is denser than the default
+    //  arena reports itself incomplete and its caller takes the waiting path)
+    const unsigned long long cap = default_arena(n_t);
+    rc = overlap_pack(job, d_t_xy, d_t_faces, idx_bytes, d_t_ids, t_begin, t_end);
     if (rc) return fail(rc);
     rc = overlap_enqueue(job, cap, d_indptr, chained != 0);
     if (rc) return fail(rc);
-    rc = enqueue_move_rows(job, d_indptr, d_indices, d_area, entry_cap, relative, s);
+    rc = enqueue_move_rows(job, d_indptr, d_indices, d_area, entry_cap, relative, job->ls);
     if (rc) return fail(rc);
     rc = overlap_request_counters(job);
     if (rc) return fail(rc);
+    if (capturing) {
+        scratch_set_capturing(false);
+        cudaError_t e = cudaStreamEndCapture(job->ls, &job->graph);
+        job->ls = s;
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&job->graph_exec, job->graph, 0);
+        if (e != cudaSuccess) {
+            // (nothing has been enqueued; fail() with capturing still set would end the capture twice)
+            if (getenv("XG_GRAPH_DEBUG")) fprintf(stderr, "[xg] end of capture / instantiate failed: %s\n", cudaGetErrorString(e));
+            cudaGetLastError();
+            capturing = false;
+            delete job;
+            return xg_overlap_run(source, d_t_xy, n_t_node, d_t_faces, idx_bytes, n_t_face, k_t, d_t_ids, t_begin, t_end,
+                                  flags & ~XG_RUN_GRAPH, d_indptr, d_indices, d_area, entry_cap, relative, stream, job_out);
+        }
+        capturing = false;
+        e = cudaGraphLaunch(job->graph_exec, s);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "cudaGraphLaunch(overlap job)", __FILE__, __LINE__));
+        job->h_stats[7] = 1;  // launched as a graph
+    }
     {
         cudaError_t e = cudaEventCreateWithFlags(&job->done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventRecord(job->done, s);

@@ -18,6 +18,16 @@ struct PackedMesh {
     uint8_t *nvert = nullptr;  // vertex count | 0x80 if the face was flipped
 };
 
+// scratch of pack_mesh handed in by a caller that must not allocate while it enqueues (a job
+// being recorded into a CUDA graph); sizes: n keys / ids, pack_sort_tmp_bytes(n) for the sort
+struct PackScratch {
+    uint32_t *keys_in = nullptr, *keys_out = nullptr;
+    int32_t *ids_in = nullptr;
+    void *sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+};
+size_t pack_sort_tmp_bytes(int64_t n);
+
 // d_frame: device pointer to [xmin, xmax, ymin, ymax] used to quantise the
 // Morton keys; d_diag2 (optional): running max of squared bbox diagonals.
 // d_clip_box (device, [xmin, xmax, ymin, ymax]) + d_kept (optional): only faces whose
@@ -27,6 +37,7 @@ int pack_mesh(const double *d_xy, const void *d_faces, int idx_bytes, int64_t f_
               int64_t f_end, int k, const double *d_frame, unsigned long long *d_diag2,
               PackedMesh *out, cudaStream_t s, const double *d_clip_box = nullptr,
               unsigned long long *d_kept = nullptr, const int32_t *d_face_ids = nullptr,
-              int64_t n_node = 0);  // n_node > 0 with a clip box: cull by node outcodes first
+              int64_t n_node = 0,   // n_node > 0 with a clip box: cull by node outcodes first
+              cudaStream_t alloc_stream = nullptr, const PackScratch *scratch = nullptr);
 
 }  // namespace xg

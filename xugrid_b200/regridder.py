@@ -107,6 +107,8 @@ class UnstructuredGrid2d:
     # candidate pairs per target row the deferred path sizes its arrays for (what the
     # library's own pair arena holds by default: a job that needs more is redone)
     _ENTRIES_PER_ROW = 16
+    # jobs of a regridder go out as one CUDA graph each (celltree.intersect_faces_into)
+    _JOB_AS_GRAPH = True
     # a resident range of at least this many target rows is built as two chained jobs, so that
     # regrid() can bring the first part down under the second job.  OFF by default: measured at
     # N = 2 (5 M rows per rank) it gains nothing -- 9.59 vs 9.56 ms end to end: the second job
@@ -227,14 +229,16 @@ class UnstructuredGrid2d:
         data = torch.empty(cap, dtype=torch.float64, device=dev)
         jobs, range_events = [], []
         if target_ids is not None:
-            jobs.append(tree.intersect_faces_into(xy, faces, indptr, indices, data, relative=relative, ids=ids))
+            jobs.append(tree.intersect_faces_into(xy, faces, indptr, indices, data, relative=relative, ids=ids,
+                                                  graph=self._JOB_AS_GRAPH))
         else:
             first = ranges[0][0]
             for c, (b, e) in enumerate(ranges):
                 if chunks is not None:
                     tgt.wait_chunk(c)  # (the compute stream waits, not the host)
                 jobs.append(tree.intersect_faces_into(xy, faces, indptr[b - first: e - first + 1], indices, data,
-                                                      t_begin=b, t_end=e, relative=relative, chained=c > 0))
+                                                      t_begin=b, t_end=e, relative=relative, chained=c > 0,
+                                                      graph=self._JOB_AS_GRAPH))
                 done = torch.cuda.Event()
                 done.record()
                 range_events.append((b - first, e - first, done))

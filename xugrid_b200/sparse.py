@@ -121,6 +121,7 @@ class PendingCSR:
         self.data, self.indices, self.indptr = data, indices, indptr
         self.n, self.m = int(n), int(m)
         self._jobs, self._rebuild = list(jobs), rebuild
+        self._all_jobs = list(jobs)  # (kept for profiling: stats, phase times, graph flag)
         self._final = None
         self._complete = None
         # (row begin, row end, event recorded behind the job that writes those rows): what lets a
