@@ -339,24 +339,27 @@ def run_ours(args) -> int:
     tgt_grid = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf, device=dev)
     t_stage = time.perf_counter()
     for g in (src_grid, tgt_grid):
-        g._stage()  # pinned staging copy (int32 connectivity), made ONCE per grid, outside the timed region
+        # pinned staging copies, made ONCE per grid, outside the timed region: what one rank
+        # uploads alone travels with 24-bit connectivity entries (fewer than 2^24 - 1 nodes),
+        # what the ranks share and assemble over NVLink as int32
+        g._stage()
+        if world > 1:
+            g._stage(packed=False)
     staging_ms = (time.perf_counter() - t_stage) * 1e3
     for g in (src_grid, tgt_grid):
         g.prefetch()
     torch.cuda.synchronize()
     nbytes = lambda t: t.numel() * t.element_size()
     if world == 1:
-        h2d_bytes = sum(nbytes(t) for t in (src_grid._xy_pin, src_grid._faces_pin, tgt_grid._xy_pin,
-                                            tgt_grid._faces_pin, h["values"]))
+        h2d_bytes = src_grid.upload_nbytes() + tgt_grid.upload_nbytes() + nbytes(h["values"])
     elif args.workload == "shuffled":
         # per rank: 1/world of every array (all replicated over NVLink: a rank's targets are anywhere)
-        h2d_bytes = sum(nbytes(t) for t in (src_grid._xy_pin, src_grid._faces_pin, tgt_grid._xy_pin,
-                                            tgt_grid._faces_pin, h["values"])) // world
+        h2d_bytes = (src_grid.upload_nbytes(sharded_over=world) + tgt_grid.upload_nbytes(sharded_over=world)
+                     + nbytes(h["values"]) // world)
     else:
         # per rank: 1/world of the replicated arrays (assembled over NVLink) + its own target rows
-        h2d_bytes = (sum(nbytes(t) for t in (src_grid._xy_pin, src_grid._faces_pin, tgt_grid._xy_pin,
-                                             h["values"])) // world
-                     + nbytes(tgt_grid._faces_pin[b:e]))
+        h2d_bytes = (src_grid.upload_nbytes(sharded_over=world)
+                     + tgt_grid.upload_nbytes(face_range=(b, e), sharded_over=world) + nbytes(h["values"]) // world)
 
     def e2e_step():
         src_grid.release_device()
@@ -495,9 +498,11 @@ def run_ours(args) -> int:
             "e2e": {"value": n_t / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "note": "the grids stage their arrays ONCE per grid in pinned host memory, connectivity "
-                            "narrowed int64 -> int32 (as the reference's Ugrid2d.__init__ copies its connectivity "
-                            "once); that one-off host work is outside the timed region and h2d_bytes counts the "
-                            "int32 bytes that really cross PCIe every step",
+                            "narrowed from int64 to 24-bit entries (meshes of fewer than 2^24 - 1 nodes; widened "
+                            "on the device by xg_unpack_u24) or int32 (arrays that the ranks share and assemble over "
+                            "NVLink), as the reference's Ugrid2d.__init__ copies its connectivity once; that one-off "
+                            "host work is outside the timed region and h2d_bytes counts the bytes that really cross "
+                            "PCIe every step",
                     "one_off_staging_ms": staging_ms},
             # this repo's own kernels per resident step: index (bounds 3, keys, pack, tolerance, one per
             # BVH level; a culled build 4 more: target-range bounds 3 + node outcodes), overlap job

@@ -267,6 +267,15 @@ int xg_face_area(const double *d_xy, const void *d_faces, int idx_bytes, int64_t
 int xg_face_centroid(const double *d_xy, const void *d_faces, int idx_bytes, int64_t n_face,
                      int k, double *d_centroid_xy, void *stream);
 
+/* ---- connectivity transport ----------------------------------------------
+ * A connectivity whose mesh has fewer than 2^24 - 1 nodes can cross PCIe as 3 bytes per index
+ * (little-endian, 0xFFFFFF = fill) instead of 4 or 8: xg_unpack_u24 widens n_values packed
+ * indices to int32 (-1 = fill) on the device.  d_packed must be 4-byte aligned (upload whole
+ * groups of 4 indices), d_out 16-byte aligned.  The reference has no counterpart (its
+ * connectivity never leaves host memory); the grids of this package stage the packed copy once,
+ * like the reference's Ugrid2d.__init__ copies its connectivity once (ugrid2d.py:103-109). */
+int xg_unpack_u24(const void *d_packed, int64_t n_values, int32_t *d_out, void *stream);
+
 /* ---- segments against faces ----------------------------------------------
  * Replaces CellTree2d.intersect_edges as called from
  * xugrid/regrid/unstructured.py:203-215 (UnstructuredGrid2d.intersection_length,

@@ -66,6 +66,7 @@ SIGNATURES = {
     "xg_locate_points": (_int, [_vp, _vp, _i64, _dbl, _vp, _vp]),
     "xg_barycentric": (_int, [_vp, _vp, _i64, _dbl, _vp, _vp, _vp]),
     "xg_intersect_edges": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, ctypes.POINTER(_i64), _vp]),
+    "xg_unpack_u24": (_int, [_vp, _i64, _vp, _vp]),
     "xg_face_area": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp]),
     "xg_face_centroid": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp]),
     "xg_csr_apply": (_int, [_int, _dbl, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),

@@ -360,9 +360,48 @@ k_face_centroid(const double2 *__restrict__ xy, const I *__restrict__ faces, int
     cxy[f] = make_double2(aw * cx + p0.x, aw * cy + p0.y);
 }
 
+// 24-bit little-endian indices (0xFFFFFF = fill) -> int32 (-1 = fill): the transport encoding
+// of a connectivity whose mesh has fewer than 2^24 - 1 nodes (xg_unpack_u24).  One thread
+// unpacks 4 indices = three aligned 32-bit words.
+__global__ void __launch_bounds__(256)
+k_unpack_u24(const uint8_t *__restrict__ packed, int64_t n, int32_t *__restrict__ out) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // group of 4 values
+    const int64_t i = q * 4;
+    if (i >= n) return;
+    auto widen = [](uint32_t v) { return v == 0xFFFFFFu ? -1 : (int32_t)v; };
+    if (i + 4 <= n) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(packed + i * 3);
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        int4 r;
+        r.x = widen(w0 & 0xFFFFFFu);
+        r.y = widen((w0 >> 24) | ((w1 & 0xFFFFu) << 8));
+        r.z = widen((w1 >> 16) | ((w2 & 0xFFu) << 16));
+        r.w = widen(w2 >> 8);
+        *reinterpret_cast<int4 *>(out + i) = r;
+    } else {
+        for (int64_t j = i; j < n; ++j) {
+            const uint8_t *b = packed + j * 3;
+            out[j] = widen((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16));
+        }
+    }
+}
+
 }  // namespace xg
 
 using namespace xg;
+
+extern "C" int xg_unpack_u24(const void *d_packed, int64_t n_values, int32_t *d_out, void *stream) {
+    if (n_values < 0 || (n_values > 0 && (!d_packed || !d_out))) { set_error("xg_unpack_u24: invalid argument"); return XG_ERR_INVALID; }
+    if (((uintptr_t)d_packed & 3u) || ((uintptr_t)d_out & 15u)) {
+        set_error("xg_unpack_u24: the packed array must be 4-byte aligned, the output 16-byte aligned");
+        return XG_ERR_INVALID;
+    }
+    if (n_values == 0) return XG_OK;
+    k_unpack_u24<<<(unsigned)div_up(div_up(n_values, 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint8_t *)d_packed, n_values, d_out);
+    XG_CHECK_LAUNCH();
+    return XG_OK;
+}
 
 static int csr_apply_impl(int method, double percentile, const int64_t *d_indptr,
                           const int32_t *d_indices, const double *d_weights, const double *d_src,

@@ -66,6 +66,8 @@ class Ugrid2d:
         self._area = None
         self._xy_pin = None
         self._faces_pin = None
+        self._faces_pin_u24 = None
+        self._packed_d = None
         self._ready = None
         self._xy_ready = None
         self._chunks = None
@@ -107,16 +109,47 @@ class Ugrid2d:
             return torch.device("cuda", torch.cuda.current_device())
         return torch.device(self.device)
 
-    def _stage(self) -> None:
-        """Pinned host staging copy, made once per grid.  Connectivity is staged as
-        int32 whenever the node count allows it (the kernels take either width):
-        that halves the bytes every later upload moves over PCIe."""
+    # meshes of at least this many faces (and fewer than 2^24 - 1 nodes) cross PCIe with 3 bytes
+    # per connectivity entry (xg_unpack_u24 widens them on the device)
+    _PACK_MIN_FACES = 1 << 20
+
+    def _packs_u24(self) -> bool:
+        return self.n_node < (1 << 24) - 1 and self.n_face >= self._PACK_MIN_FACES
+
+    def _stage(self, packed: Optional[bool] = None) -> None:
+        """Pinned host staging copies, made once per grid.  Connectivity is staged as
+        int32 whenever the node count allows it (the kernels take either width), and for
+        large meshes of fewer than 2^24 - 1 nodes also as 24-bit little-endian entries
+        (0xFFFFFF = fill): 3 instead of 8 bytes per entry over PCIe on every later upload.
+        ``packed``: which copy is needed now (None: what ``prefetch`` will use)."""
         if self._xy_pin is None:
             self._xy_pin = torch.from_numpy(self.node_coordinates).pin_memory()
+        if packed is None:
+            packed = self._packs_u24()
+        if packed and self._faces_pin_u24 is None:
+            conn = self.face_node_connectivity
+            c32 = conn if conn.dtype == np.int32 else conn.astype(np.int32)
+            # (little-endian int32: the low three bytes; -1 becomes 0xFFFFFF)
+            b = np.ascontiguousarray(np.ascontiguousarray(c32).view(np.uint8).reshape(-1, 4)[:, :3]).reshape(-1)
+            self._faces_pin_u24 = torch.from_numpy(b).pin_memory()
+        if not packed and self._faces_pin is None:
             conn = self.face_node_connectivity
             if conn.dtype != np.int32 and self.n_node < (1 << 31):
                 conn = conn.astype(np.int32)
             self._faces_pin = torch.from_numpy(np.ascontiguousarray(conn)).pin_memory()
+
+    def upload_nbytes(self, face_range: Optional[Tuple[int, int]] = None, sharded_over: int = 1) -> int:
+        """Bytes one (re-)upload of the mesh moves over PCIe: coordinates + connectivity as it is
+        staged (``sharded_over`` ranks share the replicated arrays; a face range is not shared)."""
+        k = self.n_max_node_per_face
+        xy = self.n_node * 16
+        if face_range is None:
+            packed = self._packs_u24() and sharded_over == 1
+            per = 3 if packed else (4 if self.n_node < (1 << 31) else 8)
+            return (xy + self.n_face * k * per) // sharded_over
+        packed = self._packs_u24()
+        per = 3 if packed else (4 if self.n_node < (1 << 31) else 8)
+        return xy // sharded_over + max(0, face_range[1] - face_range[0]) * k * per
 
     def prefetch(self, n_chunks: int = 1, face_range: Optional[Tuple[int, int]] = None,
                  sharded: bool = False) -> None:
@@ -134,11 +167,14 @@ class Ugrid2d:
         NVLink."""
         if self._xy_d is not None:
             return
-        _native.lib()  # raises when there is no GPU: no CPU fallback
+        L = _native.lib()  # raises when there is no GPU: no CPU fallback
         dev = self._dev()
-        self._stage()
+        whole_sharded = sharded and face_range is None
+        packed = self._packs_u24() and not whole_sharded
+        self._stage(packed)
         copy_stream = _copy_stream(dev)
         n = self.n_face
+        k = self.n_max_node_per_face
         if sharded:
             from .distributed import sharded_upload
         if sharded and face_range is None:
@@ -162,6 +198,10 @@ class Ugrid2d:
         else:
             n_chunks = max(1, min(int(n_chunks), m)) if m > 0 else 1
             bounds = [fb + (m * c) // n_chunks for c in range(n_chunks + 1)]
+        if packed:
+            # groups of 4 entries: every piece starts at a multiple of 4 faces (a few rows before
+            # the range may come along)
+            bounds = sorted(set([bounds[0] - bounds[0] % 4] + [x - x % 4 for x in bounds[1:-1]] + [bounds[-1]]))
         with torch.cuda.stream(copy_stream):
             if sharded:
                 self._xy_d = sharded_upload(self._xy_pin, dev)
@@ -171,10 +211,14 @@ class Ugrid2d:
             self._xy_ready.record(copy_stream)
             # (name, event) of every upload milestone, for scripts/e2e_timeline.py
             self._upload_events = [("coordinates uploaded", self._xy_ready)]
-            self._faces_d = torch.empty(self._faces_pin.shape, dtype=self._faces_pin.dtype, device=dev)
+            if packed:
+                self._faces_d = torch.empty((n, k), dtype=torch.int32, device=dev)
+                self._packed_d = torch.empty(n * k * 3, dtype=torch.uint8, device=dev)
+            else:
+                self._faces_d = torch.empty(self._faces_pin.shape, dtype=self._faces_pin.dtype, device=dev)
             self._chunks = []
             for b, e in zip(bounds[:-1], bounds[1:]):
-                self._faces_d[b:e].copy_(self._faces_pin[b:e], non_blocking=True)
+                self._upload_faces(L, b, e)
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record(copy_stream)
                 self._chunks.append((b, e, ev))
@@ -182,17 +226,30 @@ class Ugrid2d:
             self._ready = self._chunks[-1][2] if self._chunks else self._xy_ready
             self._face_range = None if (fb, fe) == (0, n) else (fb, fe)
 
+    def _upload_faces(self, L, b: int, e: int) -> None:
+        """rows [b, e) of the connectivity on the current (copy) stream; b a multiple of 4 when
+        the packed copy travels"""
+        if e <= b:
+            return
+        if self._packed_d is None:
+            self._faces_d[b:e].copy_(self._faces_pin[b:e], non_blocking=True)
+            return
+        k = self.n_max_node_per_face
+        lo, hi = b * k * 3, e * k * 3
+        self._packed_d[lo:hi].copy_(self._faces_pin_u24[lo:hi], non_blocking=True)
+        _native.check(L.xg_unpack_u24(self._packed_d.data_ptr() + lo, (e - b) * k,
+                                      self._faces_d.data_ptr() + b * k * 4, _native.stream_ptr()))
+
     def _complete_upload(self) -> None:
         """After a range-limited prefetch: bring up the rest of the connectivity."""
         if self._face_range is None:
             return
         fb, fe = self._face_range
         copy_stream = _copy_stream(self._dev())
+        L = _native.lib()
         with torch.cuda.stream(copy_stream):
-            if fb > 0:
-                self._faces_d[:fb].copy_(self._faces_pin[:fb], non_blocking=True)
-            if fe < self.n_face:
-                self._faces_d[fe:].copy_(self._faces_pin[fe:], non_blocking=True)
+            self._upload_faces(L, 0, fb)
+            self._upload_faces(L, fe - fe % 4 if self._packed_d is not None else fe, self.n_face)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         torch.cuda.current_stream(self._xy_d.device).wait_event(ev)
@@ -244,6 +301,7 @@ class Ugrid2d:
         self._celltree = None
         self._xy_d = None
         self._faces_d = None
+        self._packed_d = None
         self._ready = None
         self._xy_ready = None
         self._chunks = None
