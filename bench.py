@@ -339,12 +339,9 @@ def run_ours(args) -> int:
     tgt_grid = xb.Ugrid2d(txy[:, 0], txy[:, 1], -1, tf, device=dev)
     t_stage = time.perf_counter()
     for g in (src_grid, tgt_grid):
-        # pinned staging copies, made ONCE per grid, outside the timed region: what one rank
-        # uploads alone travels with 24-bit connectivity entries (fewer than 2^24 - 1 nodes),
-        # what the ranks share and assemble over NVLink as int32
+        # pinned staging copies, made ONCE per grid, outside the timed region: the connectivity of
+        # a mesh of fewer than 2^24 - 1 nodes travels as 24-bit entries, widened on the device
         g._stage()
-        if world > 1:
-            g._stage(packed=False)
     staging_ms = (time.perf_counter() - t_stage) * 1e3
     for g in (src_grid, tgt_grid):
         g.prefetch()
@@ -499,8 +496,8 @@ def run_ours(args) -> int:
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "note": "the grids stage their arrays ONCE per grid in pinned host memory, connectivity "
                             "narrowed from int64 to 24-bit entries (meshes of fewer than 2^24 - 1 nodes; widened "
-                            "on the device by xg_unpack_u24) or int32 (arrays that the ranks share and assemble over "
-                            "NVLink), as the reference's Ugrid2d.__init__ copies its connectivity once; that one-off "
+                            "on the device by xg_unpack_u24; int32 otherwise), as the reference's Ugrid2d.__init__ "
+                            "copies its connectivity once; that one-off "
                             "host work is outside the timed region and h2d_bytes counts the bytes that really cross "
                             "PCIe every step",
                     "one_off_staging_ms": staging_ms},

@@ -31,6 +31,11 @@ def _worker(rank, world, port, order, q):
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    # (meshes this small would travel as int32: take the 24-bit transport of large meshes, which
+    #  the PCIe-parallel upload shares between the ranks too)
+    from xugrid_b200 import grid as grid_mod
+
+    grid_mod.Ugrid2d._PACK_MIN_FACES = 100
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:

@@ -144,8 +144,7 @@ class Ugrid2d:
         k = self.n_max_node_per_face
         xy = self.n_node * 16
         if face_range is None:
-            packed = self._packs_u24() and sharded_over == 1
-            per = 3 if packed else (4 if self.n_node < (1 << 31) else 8)
+            per = 3 if self._packs_u24() else (4 if self.n_node < (1 << 31) else 8)
             return (xy + self.n_face * k * per) // sharded_over
         packed = self._packs_u24()
         per = 3 if packed else (4 if self.n_node < (1 << 31) else 8)
@@ -170,7 +169,7 @@ class Ugrid2d:
         L = _native.lib()  # raises when there is no GPU: no CPU fallback
         dev = self._dev()
         whole_sharded = sharded and face_range is None
-        packed = self._packs_u24() and not whole_sharded
+        packed = self._packs_u24()
         self._stage(packed)
         copy_stream = _copy_stream(dev)
         n = self.n_face
@@ -180,7 +179,14 @@ class Ugrid2d:
         if sharded and face_range is None:
             with torch.cuda.stream(copy_stream):
                 self._xy_d = sharded_upload(self._xy_pin, dev)
-                self._faces_d = sharded_upload(self._faces_pin, dev)
+                if packed:
+                    # 1/world of the 24-bit entries per rank, assembled over NVLink, widened here
+                    self._packed_d = sharded_upload(self._faces_pin_u24, dev)
+                    self._faces_d = torch.empty((n, k), dtype=torch.int32, device=dev)
+                    _native.check(L.xg_unpack_u24(self._packed_d.data_ptr(), n * k, self._faces_d.data_ptr(),
+                                                  _native.stream_ptr()))
+                else:
+                    self._faces_d = sharded_upload(self._faces_pin, dev)
                 self._xy_ready = torch.cuda.Event(enable_timing=True)
                 self._xy_ready.record(copy_stream)
                 self._upload_events = [("mesh replicated", self._xy_ready)]
