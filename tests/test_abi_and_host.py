@@ -145,6 +145,38 @@ def test_recorded_bench_lines_follow_the_contract():
     assert ref["cpu_baseline"]["kind"] in ("port", "reference")
 
 
+def test_recorded_round2_bench_lines():
+    """round 2: the final N = 1 line (with the CPU baseline on the SAME workload) and the N = 8
+    line, whose N-rank results were checked bit for bit against one rank inside the run"""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    one = json.load(open(os.path.join(root, "profiles", "r2_bench_n1_v11.json")))
+    eight = json.load(open(os.path.join(root, "profiles", "r2_bench_n8_v14.json")))
+    for line in (one, eight):
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+            assert key in line, key
+        assert line["scaling"] == "strong" and line["warmup"] >= 3 and line["config"]["n_target_faces"] == 10003852
+        roof = line["roofline"]
+        assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12 and "binding_roof" in roof
+        assert line["e2e"]["value"] < line["value"] and line["e2e"]["h2d_bytes_per_step"] > 0
+        assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # measured DRAM traffic of the dominant kernel next to the byte model
+    assert one["roofline"]["traffic"] and 0 < one["roofline"]["frac_measured_dram"] < 1
+    # the CPU baseline ran the workload the line is labelled with
+    assert "10.0M -> 10.0M" in one["cpu_baseline"]["sample"] and one["cpu_baseline"]["cores"] >= 1
+    assert eight["n_gpus"] == 8 and eight["value"] > 4.5 * one["value"]
+    chk = eight["multi_gpu_check"]
+    assert chk["gathered_output_bit_identical_to_single_rank"] is True and chk["e2e_output_bit_identical"] is True
+    assert eight["e2e"]["d2h_bytes_per_step"] * 8 >= one["e2e"]["d2h_bytes_per_step"]  # a rank brings its own columns down
+    # the reference arm prints the SAME config as our arm (round 1 ran 4 M faces under a 10 M label)
+    ref = json.load(open(os.path.join(root, "profiles", "r2_bench_reference_arm_build_container.json")))
+    assert ref["impl"] == "reference" and ref["config"] == one["config"] and ref["metric"] == one["metric"]
+    assert ref["cpu_baseline"]["cores"] >= 1 and ref["e2e"]["h2d_bytes_per_step"] == 0
+
+
 def test_ugrid1d_and_network1d_host_logic():
     # the part of xugrid.Ugrid1d / regrid/network.py:4-38 the NetworkGridder touches
     from xugrid_b200.regridder import Network1d
