@@ -111,11 +111,22 @@ k_locate(const LocateParams P, const double2 *__restrict__ pts, const int32_t *_
                 }
             }
         } else {
+            // every lane first collects the faces whose box holds ITS point as a bit mask, then
+            // works through its own one or two hits: the polygon test runs a couple of times per
+            // leaf with most lanes busy, instead of once per child with the one to three lanes
+            // whose point happens to be in that child's box (ncu launch list of the
+            // BarycentricInterpolator build, 16.7 M points: 4.5 + 4.9 ms for the two walks)
+            unsigned hits = 0u;
             while (m) {
                 const int c = __ffs(m) - 1;
                 m &= m - 1;
                 const Box b = s_node[w][c];
-                if (point_in_box(px, py, b, margin)) {
+                hits |= (point_in_box(px, py, b, margin) ? 1u : 0u) << c;
+            }
+            while (__any_sync(0xffffffffu, hits != 0u)) {
+                if (hits != 0u) {
+                    const int c = __ffs(hits) - 1;
+                    hits &= hits - 1;
                     const int64_t pos = c0 + c;
                     const int32_t fid = perm[pos];
                     if (fid < best &&
