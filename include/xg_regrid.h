@@ -211,6 +211,13 @@ int xg_overlap_abort(xg_overlap *job);
  * edge) the smallest face index is returned. */
 int xg_locate_points(const xg_index *index, const double *d_points, int64_t n_point,
                      double tolerance, int32_t *d_face_index, void *stream);
+/* The same question asked only for "inside or not" -- the mask of
+ * UnstructuredGrid2d.barycentric (xugrid/regrid/unstructured.py:188-190:
+ * locate_points(...) == -1): d_face_index receives SOME face that holds the point (not
+ * necessarily the smallest index when several qualify) or -1; the walk of a point stops at its
+ * first qualifying face. */
+int xg_locate_any(const xg_index *index, const double *d_points, int64_t n_point,
+                  double tolerance, int32_t *d_face_index, void *stream);
 /* Replaces CellTree2d.compute_barycentric_weights(points, tolerance)
  * (xugrid/ugrid/ugrid2d.py:1054-1078): triangle formula when k == 3,
  * Wachspress coordinates otherwise; d_weights is (n_point, k), zero for

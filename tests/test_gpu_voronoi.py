@@ -131,3 +131,30 @@ def test_gpu_pipeline_reproduces_the_reference_weights_at_the_golden_points(xb, 
     assert np.array_equal(tgt[order], g[f"{name}_target"])
     assert np.array_equal(src[order], g[f"{name}_source"])
     assert np.allclose(w[order], g[f"{name}_weight"], rtol=1e-10, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["mixed", "delaunay", "l_tri"])
+def test_locate_any_face_gives_the_same_mask(xb, name):
+    """xg_locate_any (what the outside mask of the barycentric build asks): -1 exactly where
+    locate_points says -1; a reported face really holds the point"""
+    from xugrid_b200.celltree import CellTree2d
+
+    xy, faces = MESHES[name]()
+    dev = torch.device("cuda", 0)
+    lo, hi = xy.min(axis=0), xy.max(axis=0)
+    pts = np.random.default_rng(7).random((30000, 2)) * (hi - lo) * 1.2 + lo - 0.1 * (hi - lo)
+    m = min(200, len(xy) - 1)
+    pts = np.concatenate([pts, xy[:300], 0.5 * (xy[:m] + xy[1: m + 1]), [[np.nan, 0.0]]])  # + nodes, edge points, NaN
+    tree = CellTree2d(xy, faces, -1, device=dev)
+    exact = tree.locate_points_device(pts).cpu().numpy()
+    some = tree.locate_points_device(pts, any_face=True).cpu().numpy()
+    assert np.array_equal(exact == -1, some == -1)
+    assert int((exact == -1).sum()) > 100 and int((exact >= 0).sum()) > 10000
+    # where both found a face it is the same one unless the point sits on a shared edge or node
+    differ = np.nonzero((exact != some) & (exact >= 0))[0]
+    assert len(differ) <= 600
+    ref = oracle.CellTree2d(xy, faces, -1)
+    for i in differ[:50]:
+        # the face reported by the any-variant holds the point too: locate restricted to that face
+        one = oracle.CellTree2d(xy, faces[some[i]: some[i] + 1], -1).locate_points(pts[i: i + 1])
+        assert one[0] == 0, (i, exact[i], some[i])

@@ -64,6 +64,7 @@ SIGNATURES = {
     "xg_bary_csr_count": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, ctypes.POINTER(_i64), _vp]),
     "xg_bary_csr_fill": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "xg_locate_points": (_int, [_vp, _vp, _i64, _dbl, _vp, _vp]),
+    "xg_locate_any": (_int, [_vp, _vp, _i64, _dbl, _vp, _vp]),
     "xg_barycentric": (_int, [_vp, _vp, _i64, _dbl, _vp, _vp, _vp]),
     "xg_intersect_edges": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, ctypes.POINTER(_i64), _vp]),
     "xg_unpack_u24": (_int, [_vp, _i64, _vp, _vp]),

@@ -369,7 +369,10 @@ class CellTree2d:
         return ei.to(torch.int64).cpu().numpy(), fi.to(torch.int64).cpu().numpy(), xy.cpu().numpy()
 
     # ------------------------------------------------------------------ points
-    def locate_points_device(self, points: ArrayLike, tolerance: Optional[float] = None) -> torch.Tensor:
+    def locate_points_device(self, points: ArrayLike, tolerance: Optional[float] = None,
+                             any_face: bool = False) -> torch.Tensor:
+        """``any_face=True``: only "inside or not" matters to the caller -- the answer is SOME
+        face that holds the point (or -1), found by a walk that stops at the first hit."""
         L = _native.lib()
         with torch.cuda.device(self.device):
             p = to_device(points, torch.float64, self.device)
@@ -377,10 +380,8 @@ class CellTree2d:
                 raise ValueError("points must have shape (n_point, 2)")
             out = torch.empty(p.shape[0], dtype=torch.int32, device=self.device)
             tol = -1.0 if tolerance is None else float(tolerance)
-            _native.check(
-                L.xg_locate_points(self._h, _native.ptr(p), int(p.shape[0]), tol, _native.ptr(out),
-                                   _native.stream_ptr())
-            )
+            fn = L.xg_locate_any if any_face else L.xg_locate_points
+            _native.check(fn(self._h, _native.ptr(p), int(p.shape[0]), tol, _native.ptr(out), _native.stream_ptr()))
         return out
 
     def locate_points(self, points: ArrayLike, tolerance: Optional[float] = None) -> np.ndarray:

@@ -52,6 +52,10 @@ __device__ __forceinline__ bool point_in_box(double px, double py, const Box &b,
 
 // lane = point (Morton order).  Writes the caller's face id (or -1) at the
 // point's original position, and the face's sorted position in pos_out.
+// ANY: the caller only asks WHETHER a face holds the point (the outside mask of the barycentric
+// build): a lane stops at its first qualifying face, subtrees that only found lanes reach are
+// not descended, and the warp leaves the walk as soon as all its points are placed.
+template <bool ANY>
 __global__ void __launch_bounds__(LOC_WARPS * 32)
 k_locate(const LocateParams P, const double2 *__restrict__ pts, const int32_t *__restrict__ order,
          int64_t n, const double2 *__restrict__ poly, const uint8_t *__restrict__ nvert, int k,
@@ -84,7 +88,9 @@ k_locate(const LocateParams P, const double2 *__restrict__ pts, const int32_t *_
     int sp = 1;
     if (lane == 0) s_stack[w][0] = P.top << 27;
     __syncwarp();
+    const bool searchable = valid && px == px && py == py;
     while (sp > 0) {
+        if (ANY && __all_sync(0xffffffffu, best_pos >= 0 || !searchable)) break;
         const int32_t entry = s_stack[w][--sp];
         const int d = entry >> 27;
         const int64_t c0 = (int64_t)(entry & 0x7ffffff) * FANOUT;
@@ -100,12 +106,13 @@ k_locate(const LocateParams P, const double2 *__restrict__ pts, const int32_t *_
         if (m == 0) continue;
         s_node[w][lane] = mine;
         __syncwarp();
+        const bool looking = !(ANY && best_pos >= 0);  // (a placed point asks for nothing more)
         if (d > 1) {
             while (m) {
                 const int c = __ffs(m) - 1;
                 m &= m - 1;
                 const Box b = s_node[w][c];
-                if (__any_sync(0xffffffffu, point_in_box(px, py, b, margin))) {
+                if (__any_sync(0xffffffffu, looking && point_in_box(px, py, b, margin))) {
                     if (lane == 0) s_stack[w][sp] = ((d - 1) << 27) | (int32_t)(c0 + c);
                     ++sp;
                 }
@@ -121,7 +128,7 @@ k_locate(const LocateParams P, const double2 *__restrict__ pts, const int32_t *_
                 const int c = __ffs(m) - 1;
                 m &= m - 1;
                 const Box b = s_node[w][c];
-                hits |= (point_in_box(px, py, b, margin) ? 1u : 0u) << c;
+                hits |= ((looking && point_in_box(px, py, b, margin)) ? 1u : 0u) << c;
             }
             while (__any_sync(0xffffffffu, hits != 0u)) {
                 if (hits != 0u) {
@@ -133,6 +140,7 @@ k_locate(const LocateParams P, const double2 *__restrict__ pts, const int32_t *_
                         point_in_polygon_or_on_edge(px, py, poly + pos * k, nvert[pos] & 0x7f, tol2)) {
                         best = fid;
                         best_pos = (int32_t)pos;
+                        if (ANY) hits = 0u;
                     }
                 }
             }
@@ -309,7 +317,7 @@ k_intersect_edges(const LocateParams P, const double4 *__restrict__ edges, const
 }
 
 static int locate_impl(const xg_index *ix, const double *d_points, int64_t n, double tol,
-                       int32_t *d_face, int32_t *d_pos, cudaStream_t s) {
+                       int32_t *d_face, int32_t *d_pos, cudaStream_t s, bool any_face = false) {
     if (n == 0) return XG_OK;
     if (ix->n_face == 0) {
         XG_CUDA(cudaMemsetAsync(d_face, 0xff, sizeof(int32_t) * (size_t)n, s));
@@ -335,9 +343,14 @@ static int locate_impl(const xg_index *ix, const double *d_points, int64_t n, do
     for (int l = 0; l < ix->n_levels; ++l) { P.boxes[l + 1] = ix->level_box[l]; P.count[l + 1] = ix->level_n[l]; }
     P.top = ix->n_levels + 1;
     const unsigned tiles = (unsigned)div_up(n, 32);
-    k_locate<<<(unsigned)div_up(tiles, LOC_WARPS), LOC_WARPS * 32, 0, s>>>(
-        P, (const double2 *)d_points, order.as<int32_t>(), n, (const double2 *)ix->poly, ix->nvert,
-        ix->k, ix->perm, tol, d_face, d_pos);
+    if (any_face)
+        k_locate<true><<<(unsigned)div_up(tiles, LOC_WARPS), LOC_WARPS * 32, 0, s>>>(
+            P, (const double2 *)d_points, order.as<int32_t>(), n, (const double2 *)ix->poly, ix->nvert,
+            ix->k, ix->perm, tol, d_face, d_pos);
+    else
+        k_locate<false><<<(unsigned)div_up(tiles, LOC_WARPS), LOC_WARPS * 32, 0, s>>>(
+            P, (const double2 *)d_points, order.as<int32_t>(), n, (const double2 *)ix->poly, ix->nvert,
+            ix->k, ix->perm, tol, d_face, d_pos);
     XG_CHECK_LAUNCH();
     return XG_OK;
 }
@@ -357,6 +370,19 @@ extern "C" int xg_locate_points(const xg_index *index, const double *d_points, i
     const double tol = tolerance < 0 ? index->default_tolerance : tolerance;
     index_note_use(index, (cudaStream_t)stream);
     return locate_impl(index, d_points, n_point, tol, d_face_index, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int xg_locate_any(const xg_index *index, const double *d_points, int64_t n_point,
+                             double tolerance, int32_t *d_face_index, void *stream) {
+    if (!index || n_point < 0 || (n_point > 0 && (!d_points || !d_face_index))) {
+        set_error("xg_locate_any: invalid argument");
+        return XG_ERR_INVALID;
+    }
+    if (n_point >= (int64_t)1 << 31) { set_error("xg_locate_any: more than 2^31 points"); return XG_ERR_UNSUPPORTED; }
+    if (tolerance < 0) { const int rc = index_host_values(index); if (rc) return rc; }
+    const double tol = tolerance < 0 ? index->default_tolerance : tolerance;
+    index_note_use(index, (cudaStream_t)stream);
+    return locate_impl(index, d_points, n_point, tol, d_face_index, nullptr, (cudaStream_t)stream, true);
 }
 
 extern "C" int xg_barycentric(const xg_index *index, const double *d_points, int64_t n_point,

@@ -289,7 +289,8 @@ class UnstructuredGrid2d:
         topo = voronoi.voronoi_topology_device(faces, xy, grid.centroids_device)
         vor_tree = CellTree2d(topo.vertices, topo.faces, -1, device=xy.device)
         polygon_index, weights = vor_tree.compute_barycentric_weights_device(points, tolerance)
-        source_face = grid.celltree.locate_points_device(points)
+        # (only "inside the source mesh or not" is asked: unstructured.py:188-190)
+        source_face = grid.celltree.locate_points_device(points, any_face=True)
         indptr, indices, data = voronoi.weights_to_csr_device(topo, polygon_index, weights, source_face)
         return MatrixCSR(data, indices, indptr, int(points.shape[0]), self.size, int(data.numel()))
 
