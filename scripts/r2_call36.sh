@@ -3,7 +3,7 @@
 export PATH=/usr/local/cuda/bin:$PATH
 export PYTHONPATH=$PWD:$PYTHONPATH
 mkdir -p gpurun_out
-timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/c36_bary_launches.csv python scripts/bary_timeline.py > gpurun_out/c36.log 2>&1
+timeout 60 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/c36_bary_launches.csv python scripts/bary_timeline.py > gpurun_out/c36.log 2>&1
 tail -3 gpurun_out/c36.log
 python - <<'PY'
 import csv, collections
